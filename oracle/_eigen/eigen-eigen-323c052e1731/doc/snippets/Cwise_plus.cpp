@@ -1,0 +1,2 @@
+Array3d v(1,2,3);
+cout << v+5 << endl;

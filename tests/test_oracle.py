@@ -1,0 +1,157 @@
+"""Pin the CPU oracle (oracle/sw_oracle.c) against the reference's own known answers and against the
+golden vectors dumped from the compiled reference (tests/golden/make_golden.py).  CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import pyoracle as o
+import synth
+from conftest import GOLDEN, read_golden_csv
+
+
+# ---- the reference's own unit tests -------------------------------------------------------------------
+def test_known_answer_score_pos():
+    """test/test_localaligner.cpp:8-27: SWAligner<Skewed>("GGTTGACTA","TGTTACGG") -> score 13, pos 2."""
+    for mode in (o.MODE_SAT_U8, o.MODE_EXACT):
+        r = o.align("GGTTGACTA", "TGTTACGG", mode=mode)
+        assert (r["score"], r["pos"]) == (13, 2)
+
+
+def test_known_answer_consensus():
+    """test/test_localaligner.cpp:53-59: consensus_x "CAGTTG", consensus_y "CA-TTG" (end -> start)."""
+    for mode in (o.MODE_SAT_U8, o.MODE_EXACT):
+        r = o.align("GGTTGACTA", "TGTTACGG", mode=mode)
+        assert (r["cx"], r["cy"]) == ("CAGTTG", "CA-TTG")
+
+
+def test_known_answer_matrix():
+    """test/test_localaligner.cpp:31-42 (commented-out golden H for the Wikipedia pair)."""
+    want = np.array([
+        [0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 3, 1, 0, 0, 0, 3, 3],
+        [0, 0, 3, 1, 0, 0, 0, 3, 6],
+        [0, 3, 1, 6, 4, 2, 0, 1, 4],
+        [0, 3, 1, 4, 9, 7, 5, 3, 2],
+        [0, 1, 6, 4, 7, 6, 4, 8, 6],
+        [0, 0, 4, 3, 5, 10, 8, 6, 5],
+        [0, 0, 2, 1, 3, 8, 13, 11, 9],
+        [0, 3, 1, 5, 4, 6, 11, 10, 8],
+        [0, 1, 0, 3, 2, 7, 9, 8, 7]], dtype=np.int32)
+    for mode in (o.MODE_SAT_U8, o.MODE_EXACT):
+        assert (o.matrix("GGTTGACTA", "TGTTACGG", mode=mode) == want).all()
+
+
+def test_index_round_trip():
+    """test/test_skewedmatrix.cpp:5-37: raw2true o true2raw = id for a 9x7 pair, both orientations."""
+    for (m, n) in ((9, 7), (7, 9)):
+        seen = set()
+        for ti in range(n + 1):
+            for tj in range(m + 1):
+                ri, rj = o.true2raw(ti, tj, m, n)
+                assert o.raw2true(ri, rj, m, n) == (ti, tj)
+                seen.add((ri, rj))
+        assert len(seen) == (m + 1) * (n + 1)
+
+
+def test_skewed_equals_plain_cells():
+    """test/test_skewedmatrix.cpp:39-66: every cell of the two SMTs agrees for GGTTGACTA / TGTTACG."""
+    for x, y in (("GGTTGACTA", "TGTTACG"), ("TGTTACG", "GGTTGACTA")):
+        assert (o.matrix(x, y, mode=o.MODE_SAT_U8) == o.matrix(x, y, mode=o.MODE_EXACT)).all()
+
+
+def test_make_string_range_values():
+    """plocalaligner.cpp:44-67; values from SURVEY §8a-9 (probed on the reference)."""
+    assert o.make_string_range(4, 125, 4980, 2.0) == [(0, 1432), (1182, 2614), (2364, 3796), (3546, 4980)]
+    r17 = o.make_string_range(17, 125, 4980, 2.0)
+    assert r17[0] == (0, 528) and r17[1] == (278, 806) and r17[-1] == (4448, 4980) and len(r17) == 17
+    assert o.make_string_range(1, 10, 100, 2.0) == [(0, 100)]
+    assert o.make_string_range(4, 100, 150, 2.0) == -1  # assert(overlaplength <= piecelength) :52
+
+
+def test_saturate():
+    """similaritymatrix.cpp:376-384."""
+    assert [o.saturate(v) for v in (-1.0, 0.0, 2.9, 3.0, 255.0, 255.5, 1000.0)] == [0, 0, 2, 3, 255, 255, 255]
+
+
+# ---- golden vectors dumped from the compiled reference ----------------------------------------------------
+def test_golden_files_intact():
+    with open(os.path.join(GOLDEN, "SHA256SUMS")) as f:
+        for line in f:
+            h, rel = line.split()
+            with open(os.path.join(GOLDEN, rel), "rb") as g:
+                assert hashlib.sha256(g.read()).hexdigest() == h, rel
+
+
+@pytest.mark.parametrize("name,mode,npiece", [("data_small_sw_skewed.csv", o.MODE_SAT_U8, 0), ("data_small_p4.csv", o.MODE_SAT_U8, 4),
+                                              ("data_small_p17.csv", o.MODE_SAT_U8, 17), ("data_small_sw_float.csv", o.MODE_EXACT, 0)])
+def test_data_small_against_reference(data_small, name, mode, npiece):
+    """BASELINE configs 1 and 2: all 1170 data_small reads, (score, pos, consensus) identical to the reference."""
+    ref, truth = data_small
+    gold = read_golden_csv(name)
+    assert len(gold) == len(truth) == 1170
+    step = 1 if mode == o.MODE_SAT_U8 else 6  # the int32 EXACT fill is slower; every 6th read keeps the CPU suite short
+    for (idx, _, seq, _), g in list(zip(truth, gold))[::step]:
+        r = o.align_chunked(seq, ref, npiece, 2.0, mode=mode) if npiece else o.align(seq, ref, mode=mode)
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (g["score"], g["pos"], g["cx"], g["cy"]), idx
+
+
+def test_data_small_scores_saturate(data_small):
+    """every data_small read scores exactly 255 on the u8 path."""
+    assert all(g["score"] == 255 for g in read_golden_csv("data_small_sw_skewed.csv"))
+
+
+def test_random_pairs_against_reference(random_pairs):
+    for c in random_pairs:
+        sc = c["scoring"]
+        mode = o.MODE_SAT_U8 if c["smt"] == 0 else o.MODE_EXACT
+        kw = dict(mode=mode, match=sc["match"], mismatch=sc["mismatch"], gap=sc["gap"])
+        r = o.align_chunked(c["x"], c["y"], c["npiece"], c["ratio"], **kw) if c["npiece"] else o.align(c["x"], c["y"], **kw)
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (c["score"], c["pos"], c["cx"], c["cy"]), (len(c["x"]), len(c["y"]), c["smt"], sc, c["npiece"])
+
+
+def test_c3_sample_against_reference(c3_sample):
+    ref = synth.c3_reference(c3_sample["ref_len"])
+    assert hashlib.sha256(ref.encode()).hexdigest() == c3_sample["ref_sha256"]
+    for e in c3_sample["reads"][:4]:  # 150 x 10^6 int32 cells each; 4 keep the CPU suite short
+        r = o.align(e["x"], ref, mode=o.MODE_SAT_U8)
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (e["score"], e["pos"], e["cx"], e["cy"])
+
+
+def test_c4_sample_against_reference(c4_sample):
+    table = synth.blosum62_table()
+    for e in c4_sample["entries"]:
+        r = o.align(e["x"], c4_sample["query"], mode=o.MODE_EXACT, table=table, gap=c4_sample["gap"])
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (e["score"], e["pos"], e["cx"], e["cy"])
+
+
+@pytest.mark.skipif(o.ref() is None or not os.path.isdir("/root/reference"), reason="compiled reference not available")
+def test_live_reference_random_cells():
+    """Cell-by-cell: restatement == reference operator()(row, col) on fresh random non-square shapes."""
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        m, n = int(rng.integers(1, 90)), int(rng.integers(1, 140))
+        if m == n:
+            n += 1
+        x = "".join(rng.choice(list("ACGT"), size=m))
+        y = "".join(rng.choice(list("ACGT"), size=n))
+        for smt, mode in ((0, o.MODE_SAT_U8), (1, o.MODE_EXACT)):
+            want = o.ref_matrix(x, y, smt=smt, scoring_kind=1, match=4, mismatch=-2, gap=3).astype(np.int32)
+            got = o.matrix(x, y, mode=mode, match=4, mismatch=-2, gap=3)
+            assert (want == got).all(), (m, n, smt)
+
+
+@pytest.mark.skipif(o.ref() is None or not os.path.isdir("/root/reference"), reason="compiled reference not available")
+def test_live_reference_saturating_scores():
+    """Saturation with a large match score (hits 255 within a few rows) and scoring clamp sat()."""
+    rng = np.random.default_rng(8)
+    for _ in range(40):
+        m, n = int(rng.integers(20, 70)), int(rng.integers(80, 200))
+        y = "".join(rng.choice(list("ACGT"), size=n))
+        s = int(rng.integers(0, n - m))
+        x = y[s:s + m]
+        want = o.ref_align(x, y, smt=0, scoring_kind=1, match=40, mismatch=-7, gap=9)
+        got = o.align(x, y, mode=o.MODE_SAT_U8, match=40, mismatch=-7, gap=9)
+        assert (got["score"], got["pos"], got["cx"], got["cy"]) == (want["score"], want["pos"], want["cx"], want["cy"])
+        assert got["score"] == 255
