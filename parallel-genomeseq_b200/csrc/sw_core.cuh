@@ -1,0 +1,563 @@
+// sw_core.cuh — sm_100a Smith-Waterman wavefront core (device code).
+//
+// Replaces, for the alignment hot path of kosta777/parallel-genomeseq (citations relative to
+// /root/reference/):
+//   Similarity_Matrix_Skewed::iterate        src/aligner/similaritymatrix.cpp:386-561   (SAT_U8 mode)
+//   Similarity_Matrix::iterate               src/aligner/similaritymatrix.cpp:99-116,247-257 (EXACT mode)
+//   ..::find_index_of_maximum                src/aligner/similaritymatrix.cpp:291-299 / :21-28
+//   SWAligner::traceback                     src/aligner/smithwaterman.cpp:40-78
+//
+// Design (B200-first, not a port of the AVX2 skewed-matrix code):
+//   * The full H matrix is never materialised.  A "pair" packs TWO alignments against the same
+//     y-range into the two signed 16-bit halves of every 32-bit register (s16x2); one DP cell pair
+//     costs four DPX instructions (VIADDMNMX.S16x2[.RELU], VIMNMX.S16x2) — see step() below.
+//   * L lanes (a power of two, a sub-warp "group") stripe the rows of one pair, R rows per lane in
+//     registers.  Lane g works on column j = t - g at step t (a skewed wavefront); the row carry
+//     between neighbouring lanes is one __shfl_up_sync per step.
+//   * Values are carried as E = H - G (G = gap penalty): then
+//         d    = max(E_nw + (s+G), E_w, 0)            one VIADDMNMX.S16x2.RELU   (= max(NW+s, W-G, 0))
+//         dG   = min(d - G, 255 - G)                  one VIADDMNMX (min form)   (u8 saturation, SAT_U8)
+//         E    = max(E_n - G, dG)                     one VIADDMNMX              (= H - G)
+//         bmax = max(bmax, E)                         one VIMNMX.S16x2
+//   * Every B steps each lane flushes its block maximum and checkpoints its register state
+//     (R+1 words).  Pass 2 (locate + traceback) restarts the same wavefront from a checkpoint, so the
+//     arg-max tie-break of the reference and its value-greedy traceback are reproduced exactly while
+//     only O(B * m) cells are ever recomputed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace swb {
+
+constexpr int MODE_SAT_U8 = 0;
+constexpr int MODE_EXACT = 1;
+
+// One packed pair of alignments (halves A = low 16 bits, B = high 16 bits).
+struct PairDesc {
+  uint32_t q_off;     // word offset into qpairs: L*R packed rows
+  uint32_t y_off;     // first y position of this pair's range (0-based)
+  uint32_t n;         // columns in the range
+  uint32_t nblk;      // ceil((n + L) / B) blocks of B steps
+  uint32_t mA, mB;    // real row counts (0 = empty half)
+  uint32_t xA, xB;    // byte offsets of the raw sequences in reads_raw
+  uint64_t blk_off;   // word offset into blkmax: nblk * L words
+  uint64_t ck_off;    // word offset into ckpt  : nblk * (R+1) * L words
+};
+
+struct Scoring {
+  uint32_t negG2;     // pack(-G, -G)
+  uint32_t sel_and;   // (s_match+G) ^ (s_mismatch+G), both halves
+  uint32_t sel_xor;   // pack(s_mismatch+G, ...)
+  uint32_t ceil2;     // pack(255-G, 255-G)   (SAT_U8)
+  int32_t G;
+};
+
+struct PassParams {
+  const uint8_t* ref_raw;      // y bytes
+  const uint8_t* ref_code;     // y alphabet codes (profile select)
+  const uint8_t* reads_raw;    // concatenated x bytes
+  const uint32_t* qpairs;      // packed per-row symbols (compare select) or x bytes (profile select)
+  const int16_t* table;        // [256][KP] (s + G) per (x byte, y code), profile select
+  int KP;                      // y alphabet size + 1 (sentinel code = KP-1)
+  const PairDesc* pairs;
+  int npairs;
+  uint32_t* blkmax;
+  uint32_t* ckpt;
+  int L, logL, B, logB;
+  Scoring sc;
+};
+
+// ---- DPX / packed-half primitives -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t hset2_eq(uint32_t a, uint32_t b) {
+  // HSET2.EQ: per 16-bit half 0xFFFF where the halves are equal (operands: SYM_BASE | symbol).
+  uint32_t r;
+  asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
+
+constexpr uint32_t NEG_INF2 = 0x80008000u;   // pack(-32768, -32768)
+// Symbols are compared as fp16 bit patterns by HSET2; 0x4000 | byte is a NORMAL fp16 number (2.0 .. 2.5),
+// so the comparison never touches subnormals, signed zeros or NaNs.
+constexpr uint32_t SYM_BASE = 0x4000u;
+constexpr uint32_t SENT_Y = SYM_BASE | 0x0100u;   // never equals a byte symbol
+constexpr uint32_t SENT_X = SYM_BASE | 0x0101u;   // never equals a byte symbol nor SENT_Y
+
+// Per-lane register state of the wavefront for one pair.
+template <int R>
+struct LaneState {
+  uint32_t E[R];      // H - G of this lane's R rows at the previous column
+  uint32_t up_prev;   // H - G of the row above this lane's first row at the previous column
+};
+
+// Symbol selection: returns pack(s+G) for row k against the current column.
+template <int R>
+struct CompareSelect {
+  uint32_t q[R];      // pack(xA[row], xB[row]) raw bytes or sentinels
+  uint32_t r2;        // pack(y[j], y[j]) for the current column
+  uint32_t sel_and, sel_xor;
+  __device__ __forceinline__ void set_column(uint32_t ycode) { r2 = ycode * 0x00010001u; }
+  __device__ __forceinline__ uint32_t operator()(int k) const { return (hset2_eq(q[k], r2) & sel_and) ^ sel_xor; }
+};
+
+// Profile selection: per-warp query profile in shared memory, word index ((code*R + k)*32 + lane).
+template <int R>
+struct ProfileSelect {
+  const uint32_t* prof;   // shared memory, already offset by lane
+  const uint32_t* col;
+  __device__ __forceinline__ void set_column(uint32_t ycode) { col = prof + ycode * (R * 32); }
+  __device__ __forceinline__ uint32_t operator()(int k) const { return col[k * 32]; }
+};
+
+// One wavefront step for one lane: column j of rows [g*R, (g+1)*R).  Hook sees every new cell.
+//   hook(k, E_new, diag, E_old, up_in) with all values in E-space (H - G), packed s16x2.
+template <int R, bool SAT, class Select, class Hook>
+__device__ __forceinline__ void step(LaneState<R>& st, const Select& sel, const Scoring& sc, uint32_t up_cur,
+                                     uint32_t& bmax, Hook&& hook) {
+  uint32_t diag = st.up_prev;
+  uint32_t up = up_cur;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t sG = sel(k);
+    const uint32_t e_old = st.E[k];
+    uint32_t d = __viaddmax_s16x2_relu(diag, sG, e_old);
+    uint32_t dG = SAT ? viaddmin_s16x2(d, sc.negG2, sc.ceil2) : __vadd2(d, sc.negG2);
+    const uint32_t e_new = __viaddmax_s16x2(up, sc.negG2, dG);
+    hook(k, e_new, diag, e_old, up);
+    diag = e_old;
+    up = e_new;
+    st.E[k] = e_new;
+    bmax = __vmaxs2(bmax, e_new);
+  }
+  st.up_prev = up_cur;
+}
+
+struct NoHook {
+  __device__ __forceinline__ void operator()(int, uint32_t, uint32_t, uint32_t, uint32_t) const {}
+};
+
+// y symbol for column j (1-based) of a pair's range, or the sentinel outside [1, n].
+template <bool PROFILE>
+__device__ __forceinline__ uint32_t load_y(const PassParams& p, const PairDesc& pd, int j) {
+  const bool in = (j >= 1) && (j <= (int)pd.n);
+  const uint32_t idx = in ? (pd.y_off + (uint32_t)(j - 1)) : pd.y_off;
+  if (PROFILE) { uint32_t c = __ldg(p.ref_code + idx); return in ? c : (uint32_t)(p.KP - 1); }
+  uint32_t c = __ldg(p.ref_raw + idx);
+  return in ? (SYM_BASE | c) : SENT_Y;
+}
+
+template <int R>
+__device__ __forceinline__ void init_state(LaneState<R>& st, const Scoring& sc) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) st.E[k] = sc.negG2;
+  st.up_prev = sc.negG2;
+}
+
+// Checkpoint layout: word ((blk*(R+1) + k) * L + g), k == R holds up_prev.
+template <int R>
+__device__ __forceinline__ void save_state(const LaneState<R>& st, uint32_t* ck, int L, int g) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) ck[k * L + g] = st.E[k];
+  ck[R * L + g] = st.up_prev;
+}
+template <int R>
+__device__ __forceinline__ void load_state(LaneState<R>& st, const uint32_t* ck, int L, int g) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) st.E[k] = ck[k * L + g];
+  st.up_prev = ck[R * L + g];
+}
+
+template <int R>
+__device__ __forceinline__ void load_compare_rows(CompareSelect<R>& sel, const PassParams& p, const PairDesc& pd, int g) {
+  const uint32_t* q = p.qpairs + pd.q_off + (uint32_t)g * R;
+#pragma unroll
+  for (int k = 0; k < R; ++k) sel.q[k] = __ldg(q + k);
+  sel.sel_and = p.sc.sel_and;
+  sel.sel_xor = p.sc.sel_xor;
+}
+
+// Build this lane's slice of the per-warp profile: prof[(code*R + k)*32 + lane] = pack(T[xA][code], T[xB][code]).
+template <int R>
+__device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassParams& p, const PairDesc& pd, int g, int lane) {
+  const uint32_t* q = p.qpairs + pd.q_off + (uint32_t)g * R;
+  for (int k = 0; k < R; ++k) {
+    const uint32_t w = __ldg(q + k);
+    const uint32_t a = (w & 0xFFFFu) - SYM_BASE, b = (w >> 16) - SYM_BASE;
+    for (int c = 0; c < p.KP; ++c) {
+      // sentinel rows (a/b >= 256) and the sentinel column use the table's last row/column: never a match
+      const int16_t sa = p.table[(a < 256 ? a : 256) * p.KP + c];
+      const int16_t sb = p.table[(b < 256 ? b : 256) * p.KP + c];
+      prof_warp[(c * R + k) * 32 + lane] = (uint32_t)(uint16_t)sa | ((uint32_t)(uint16_t)sb << 16);
+    }
+  }
+}
+
+// ======================================================================================================
+// Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp.
+// ======================================================================================================
+template <int R, bool SAT, bool PROFILE>
+__global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
+  extern __shared__ uint32_t smem_prof[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  const int L = p.L;
+  const int g = lane & (L - 1);
+  const int groups_per_warp = 32 >> p.logL;
+  int pair = gwarp * groups_per_warp + (lane >> p.logL);
+  const bool live = pair < p.npairs;
+  if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
+  const PairDesc pd = p.pairs[pair];
+
+  LaneState<R> st;
+  init_state<R>(st, p.sc);
+  CompareSelect<R> csel;
+  ProfileSelect<R> psel;
+  if (PROFILE) {
+    uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+    build_profile<R>(prof_warp, p, pd, g, lane);
+    psel.prof = prof_warp + lane;
+    __syncwarp();
+  } else {
+    load_compare_rows<R>(csel, p, pd, g);
+  }
+
+  // steps t = 1 .. n + L - 1 (lane g handles column t - g); run whole blocks so every lane flushes together
+  int steps = (int)pd.nblk << p.logB;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+
+  uint32_t* blk = p.blkmax + pd.blk_off;
+  uint32_t* ck = p.ckpt + pd.ck_off;
+  uint32_t bmax = NEG_INF2;
+  uint32_t ynext = load_y<PROFILE>(p, pd, 1 - g);
+  for (int t = 1; t <= steps; ++t) {
+    const uint32_t ycur = ynext;
+    ynext = load_y<PROFILE>(p, pd, t + 1 - g);
+    uint32_t up_cur = __shfl_up_sync(0xffffffffu, st.E[R - 1], 1, L);
+    if (g == 0) up_cur = p.sc.negG2;
+    if (PROFILE) { psel.set_column(ycur); step<R, SAT>(st, psel, p.sc, up_cur, bmax, NoHook()); }
+    else { csel.set_column(ycur); step<R, SAT>(st, csel, p.sc, up_cur, bmax, NoHook()); }
+    if ((t & (p.B - 1)) == 0) {
+      const int b = (t >> p.logB) - 1;
+      if (live && b < (int)pd.nblk) {
+        blk[(size_t)b * L + g] = bmax;
+        save_state<R>(st, ck + (size_t)b * (R + 1) * L, L, g);
+      }
+      bmax = NEG_INF2;
+    }
+  }
+}
+
+// ======================================================================================================
+// Pass 2: locate the reference's arg-max cell and trace back.  One group of L lanes per task.
+// ======================================================================================================
+struct TaskDesc {
+  uint32_t pair;      // index into pairs
+  uint32_t half;      // 0 = low half (A), 1 = high half (B)
+  uint32_t out;       // output slot (read index)
+  uint32_t pos_add;   // added to pos (left edge of the chunk, plocalaligner.cpp:137)
+};
+
+struct TraceParams {
+  PassParams pp;
+  const TaskDesc* tasks;      // indexed through task_list when non-null
+  const uint32_t* task_list;
+  int ntasks;
+  int mode;                   // MODE_SAT_U8: skewed raw-order tie-break; MODE_EXACT: column-major
+  int16_t* scratch;           // per group: Wc columns x rstride rows of H
+  int Wc, rstride;            // ring width (power of two), rows per column (L*R + 1)
+  int32_t* out_score;
+  uint32_t* out_pos;
+  uint32_t* out_end;          // 2 per task: index_x, index_y of the arg-max
+  uint8_t* out_cx;
+  uint8_t* out_cy;
+  uint32_t* out_len;
+  uint32_t cons_cap;          // bytes per task in out_cx / out_cy
+  uint32_t* out_flags;        // bit0: consensus overflowed cons_cap
+  int want_consensus;
+};
+
+__device__ __forceinline__ int half_of(uint32_t v, uint32_t half) { return (int)(int16_t)(half ? (v >> 16) : (v & 0xFFFFu)); }
+
+// Raw key of the skewed storage, _trueindex2rawindex similaritymatrix.cpp:353-364 with the constructor's
+// role swap (:274-289): ti = column j, tj = row i, len_x = n+1, len_y = m+1.  Key = (rj << 32) | ri.
+__device__ __forceinline__ uint64_t skew_key(int i, int j, int m, int n) {
+  const int len_x = n + 1, len_y = m + 1;
+  const int nrows = min(len_x, len_y), ncols = max(len_x, len_y);
+  const int ti = j, tj = i;
+  int ri, rj;
+  if (ti + tj < nrows - 1) { ri = ti; rj = ti + tj; }
+  else if (ti + tj > ncols - 1) { ri = ti - ncols + len_y; rj = ti + tj - (ncols - 1) - 1; }
+  else { ri = (len_x <= len_y) ? ti : len_y - 1 - tj; rj = ti + tj; }
+  return ((uint64_t)(uint32_t)rj << 32) | (uint32_t)ri;
+}
+__device__ __forceinline__ uint64_t colmajor_key(int i, int j) { return ((uint64_t)(uint32_t)j << 32) | (uint32_t)i; }
+
+template <int R, bool SAT, bool PROFILE>
+struct GroupCtx {
+  const PassParams& p;
+  const PairDesc& pd;
+  CompareSelect<R> csel;
+  ProfileSelect<R> psel;
+  uint32_t gmask;
+  int L, g;
+  __device__ __forceinline__ GroupCtx(const PassParams& p_, const PairDesc& pd_) : p(p_), pd(pd_) {}
+
+  // Restore the wavefront to the start of step t0 + 1 (t0 a multiple of B) and run steps t0+1 .. t1.
+  template <class Hook>
+  __device__ __forceinline__ void run(LaneState<R>& st, int t0, int t1, Hook&& hook) {
+    if (t0 == 0) init_state<R>(st, p.sc);
+    else load_state<R>(st, p.ckpt + pd.ck_off + (size_t)((t0 >> p.logB) - 1) * (R + 1) * L, L, g);
+    uint32_t bmax = NEG_INF2;
+    uint32_t ynext = load_y<PROFILE>(p, pd, t0 + 1 - g);
+    for (int t = t0 + 1; t <= t1; ++t) {
+      const uint32_t ycur = ynext;
+      ynext = load_y<PROFILE>(p, pd, t + 1 - g);
+      uint32_t up_cur = __shfl_up_sync(gmask, st.E[R - 1], 1, L);
+      if (g == 0) up_cur = p.sc.negG2;
+      const int j = t - g;
+      auto h = [&](int k, uint32_t e_new, uint32_t, uint32_t, uint32_t) { hook(k, j, e_new); };
+      if (PROFILE) { psel.set_column(ycur); step<R, SAT>(st, psel, p.sc, up_cur, bmax, h); }
+      else { csel.set_column(ycur); step<R, SAT>(st, csel, p.sc, up_cur, bmax, h); }
+    }
+  }
+};
+
+__device__ __forceinline__ uint64_t group_min_u64(uint64_t v, uint32_t gmask, int L) {
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    uint32_t lo = __shfl_xor_sync(gmask, (uint32_t)v, o), hi = __shfl_xor_sync(gmask, (uint32_t)(v >> 32), o);
+    uint64_t w = ((uint64_t)hi << 32) | lo;
+    v = w < v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ int group_max_i32(int v, uint32_t gmask, int L) {
+  for (int o = L >> 1; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
+  return v;
+}
+
+template <int R, bool SAT, bool PROFILE>
+__global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
+  extern __shared__ uint32_t smem_prof[];
+  const PassParams& p = tp.pp;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int L = p.L;
+  const int g = lane & (L - 1);
+  const int grp_in_warp = lane >> p.logL;
+  const int groups_per_warp = 32 >> p.logL;
+  const uint32_t gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp_in_warp * L));
+  const int ggroup = (blockIdx.x * (blockDim.x >> 5) + warp_in_cta) * groups_per_warp + grp_in_warp;
+  const int ngroups = gridDim.x * (blockDim.x >> 5) * groups_per_warp;
+  int16_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;
+  const int G = p.sc.G;
+
+  for (int ti = ggroup; ti < tp.ntasks; ti += ngroups) {
+    const TaskDesc td = tp.tasks[tp.task_list ? tp.task_list[ti] : ti];
+    const PairDesc pd = p.pairs[td.pair];
+    const int m = td.half ? pd.mB : pd.mA;
+    const int n = pd.n;
+    const uint32_t half = td.half;
+    const uint8_t* xraw = p.reads_raw + (td.half ? pd.xB : pd.xA);
+    const uint8_t* yraw = p.ref_raw + pd.y_off;
+
+    GroupCtx<R, SAT, PROFILE> gc(p, pd);
+    gc.gmask = gmask; gc.L = L; gc.g = g;
+    if (PROFILE) {
+      // one profile slice per warp: groups of a warp may hold different pairs, each lane fills its own slice
+      uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+      __syncwarp(gmask);
+      build_profile<R>(prof_warp, p, pd, g, lane);
+      gc.psel.prof = prof_warp + lane;
+      __syncwarp(gmask);
+    } else {
+      load_compare_rows<R>(gc.csel, p, pd, g);
+    }
+
+    // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------
+    const uint32_t* blk = p.blkmax + pd.blk_off;
+    int vmax = -32768;
+    for (uint32_t w = g; w < pd.nblk * (uint32_t)L; w += L) vmax = max(vmax, half_of(blk[w], half));
+    vmax = group_max_i32(vmax, gmask, L);
+    const int score = vmax + G;
+    if (m == 0 || score <= 0) {
+      // all-zero matrix: the reference reads H(-1,-1) (undefined); we return score 0, pos 0, "".
+      if (g == 0) {
+        tp.out_score[td.out] = 0; tp.out_pos[td.out] = 0; tp.out_len[td.out] = 0;
+        tp.out_end[2 * td.out] = 0; tp.out_end[2 * td.out + 1] = 0; tp.out_flags[td.out] = 0;
+      }
+      continue;
+    }
+
+    // ---- 2. arg-max with the reference's tie-break ----------------------------------------------------
+    // candidate blocks: some lane's block maximum equals vmax.  Cells equal to the maximum are recomputed
+    // and keyed; the smallest key wins (skewed raw order for SAT_U8, column-major for EXACT).
+    const int ncols_raw = max(n + 1, m + 1);
+    uint64_t best = ~0ull;
+    LaneState<R> st;
+    const int row0 = g * R + 1;          // first H row of this lane
+    auto scan_block = [&](int b) {
+      const int t0 = b << p.logB;
+      const int jmin = max(1, t0 + 1 - (L - 1)), jmax = min(n, t0 + p.B);
+      if (jmin > jmax) return;
+      uint64_t lb;
+      if (tp.mode == MODE_SAT_U8) lb = (jmax + m >= ncols_raw) ? 0ull : ((uint64_t)(uint32_t)(jmin + 1) << 32);
+      else lb = (uint64_t)(uint32_t)jmin << 32;
+      if (lb > best) return;             // every key in this block is larger than the current winner
+      uint64_t mine = ~0ull;
+      gc.run(st, t0, t0 + p.B, [&](int k, int j, uint32_t e_new) {
+        const int i = row0 + k;
+        if (half_of(e_new, half) == vmax && i <= m && j >= 1 && j <= n) {
+          const uint64_t key = (tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j);
+          mine = key < mine ? key : mine;
+        }
+      });
+      mine = group_min_u64(mine, gmask, L);
+      best = mine < best ? mine : best;
+    };
+    // blocks that may hold wrapped (lower-triangle) cells sort first in the skewed order: visit them first
+    int b_wrap = (int)pd.nblk;
+    if (tp.mode == MODE_SAT_U8) {
+      const int need = ncols_raw - m;                        // jmax >= need  <=> block may wrap
+      b_wrap = max(0, ((need + p.B - 1) >> p.logB) - 1);
+      if (b_wrap > (int)pd.nblk) b_wrap = (int)pd.nblk;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      const int b_lo = pass == 0 ? b_wrap : 0, b_hi = pass == 0 ? (int)pd.nblk : b_wrap;
+      for (int bb = b_lo; bb < b_hi; bb += L) {
+        const int b = bb + g;
+        bool cand = false;
+        if (b < b_hi) {
+          int bm = -32768;
+          for (int q = 0; q < L; ++q) bm = max(bm, half_of(blk[(size_t)b * L + q], half));
+          cand = (bm == vmax);
+        }
+        uint32_t cm = (__ballot_sync(gmask, cand) & gmask) >> (grp_in_warp * L);
+        while (cm) { const int q = __ffs(cm) - 1; cm &= cm - 1; scan_block(bb + q); }
+      }
+    }
+    int ie, je;
+    if (tp.mode == MODE_SAT_U8) {
+      // invert skew_key: _rawindex2trueindex, similaritymatrix.cpp:330-346
+      const int rj = (int)(best >> 32), ri = (int)(uint32_t)best;
+      const int len_x = n + 1, len_y = m + 1, nrows = min(len_x, len_y);
+      int t_i, t_j;
+      if (rj < nrows - 1) {
+        if (ri <= rj) { t_i = ri; t_j = rj - ri; } else { t_i = len_x - nrows + ri; t_j = len_y - ri + rj; }
+      } else {
+        if (len_x <= len_y) { t_i = ri; t_j = rj - ri; } else { t_i = rj - (nrows - 1) + ri; t_j = nrows - 1 - ri; }
+      }
+      je = t_i; ie = t_j;
+    } else { je = (int)(best >> 32); ie = (int)(uint32_t)best; }
+
+    if (g == 0) {
+      tp.out_score[td.out] = score;
+      tp.out_end[2 * td.out] = (uint32_t)ie; tp.out_end[2 * td.out + 1] = (uint32_t)je;
+    }
+
+    // ---- 3. traceback over a ring of recomputed columns ---------------------------------------------
+    // SWAligner::traceback, smithwaterman.cpp:40-78, literally: compare the three neighbours' VALUES.
+    int ix = ie, iy = je;
+    uint32_t len = 0, flags = 0, pos = 0;
+    uint8_t* cx = tp.out_cx + (size_t)td.out * tp.cons_cap;
+    uint8_t* cy = tp.out_cy + (size_t)td.out * tp.cons_cap;
+    const int wmask = tp.Wc - 1;
+    bool done = false;
+    while (!done) {
+      const int l_e = (ix - 1) / R;
+      const int t_hi = iy + l_e;
+      // restart point: a checkpoint at or before column iy - 2 - lookback (lookback: the rows still above us)
+      int c_lo = iy - 2 - (ix + 8);
+      if (c_lo < 0) c_lo = 0;
+      const int t_lo = (c_lo >> p.logB) << p.logB;
+      const int valid_lo = max(t_lo, t_hi - tp.Wc + 1);     // oldest column every lane still holds
+      if (t_lo > 0) {
+        // the checkpoint itself is column t_lo - g of this lane's rows
+        LaneState<R> ck; load_state<R>(ck, p.ckpt + pd.ck_off + (size_t)((t_lo >> p.logB) - 1) * (R + 1) * L, L, g);
+        const int jc = t_lo - g;
+        if (jc >= 0) {
+#pragma unroll
+          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + row0 + k] = (int16_t)(half_of(ck.E[k], half) + G);
+        }
+      }
+      gc.run(st, t_lo, t_hi, [&](int k, int j, uint32_t e_new) {
+        if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + row0 + k] = (int16_t)(half_of(e_new, half) + G);
+      });
+      __syncwarp(gmask);
+      if (g == 0) {
+        // row 0 and column 0 of H are zero and never stored
+        auto Hat = [&](int i, int j) -> int {
+          if (i <= 0 || j <= 0) return 0;
+          return (int)((volatile int16_t*)scr)[(size_t)(j & wmask) * tp.rstride + i];
+        };
+        while (true) {
+          if (iy - 1 < valid_lo && iy - 1 > 0) break;        // window exhausted: recompute further left
+          const int n1 = Hat(ix - 1, iy - 1), n2 = Hat(ix, iy - 1), n3 = Hat(ix - 1, iy);
+          if (len >= tp.cons_cap) { flags |= 1u; done = true; break; }
+          if (n1 == 0 || n2 == 0 || n3 == 0) {
+            if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = yraw[iy - 1]; }
+            ++len; pos = (uint32_t)iy; done = true; break;
+          }
+          if (n1 >= n2 && n1 >= n3) { if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = yraw[iy - 1]; } --ix; --iy; }
+          else if (n2 >= n1 && n2 >= n3) { if (tp.want_consensus) { cx[len] = '-'; cy[len] = yraw[iy - 1]; } --iy; }
+          else { if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = '-'; } --ix; }
+          ++len;
+        }
+      }
+      // broadcast the walker's state to the group
+      const int src = grp_in_warp * L;
+      ix = __shfl_sync(gmask, ix, src); iy = __shfl_sync(gmask, iy, src);
+      done = __shfl_sync(gmask, (int)done, src) != 0;
+      __syncwarp(gmask);
+    }
+    if (g == 0) {
+      tp.out_pos[td.out] = pos + td.pos_add;
+      tp.out_len[td.out] = len;
+      tp.out_flags[td.out] = flags;
+    }
+  }
+}
+
+// ======================================================================================================
+// Small helper kernels
+// ======================================================================================================
+// qpairs[q_off + row] = pack(symA(row), symB(row)); rows beyond a half's length hold SENT_X.
+__global__ void pack_rows_kernel(const uint8_t* reads_raw, const PairDesc* pairs, int npairs, int rows_per_pair, uint32_t* qpairs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)npairs * rows_per_pair;
+  if (idx >= total) return;
+  const int pair = (int)(idx / rows_per_pair), row = (int)(idx % rows_per_pair);
+  const PairDesc pd = pairs[pair];
+  const uint32_t a = row < (int)pd.mA ? (SYM_BASE | reads_raw[pd.xA + row]) : SENT_X;
+  const uint32_t b = row < (int)pd.mB ? (SYM_BASE | reads_raw[pd.xB + row]) : SENT_X;
+  qpairs[pd.q_off + row] = a | (b << 16);
+}
+
+// Per-task maximum (E-space + G = score) from the block maxima; used by the chunked path to pick the
+// best piece (plocalaligner.cpp:122-129) before any traceback.
+__global__ void task_max_kernel(const PairDesc* pairs, const TaskDesc* tasks, int ntasks, const uint32_t* blkmax, int L, int G, int32_t* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntasks) return;
+  const TaskDesc td = tasks[t];
+  const PairDesc pd = pairs[td.pair];
+  const uint32_t* blk = blkmax + pd.blk_off;
+  int v = -32768;
+  for (uint32_t w = 0; w < pd.nblk * (uint32_t)L; ++w) v = max(v, half_of(blk[w], td.half));
+  const int m = td.half ? pd.mB : pd.mA;
+  out[t] = (m == 0) ? -1 : max(v + G, 0);
+}
+
+// Lowest-index piece with the strictly greatest maximum (serial semantic of plocalaligner.cpp:122-129).
+__global__ void select_piece_kernel(const int32_t* task_max, int nreads, int npiece, uint32_t* winner_task) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nreads) return;
+  int best = -1, bp = 0;      // max_score_l = -1.0, max_score_piece = 0  (:107-108)
+  for (int pc = 0; pc < npiece; ++pc) {
+    const int v = task_max[(size_t)r * npiece + pc];
+    if (v > best) { best = v; bp = pc; }
+  }
+  winner_task[r] = (uint32_t)(r * npiece + bp);
+}
+
+}  // namespace swb

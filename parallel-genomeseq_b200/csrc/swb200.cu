@@ -1,0 +1,733 @@
+// swb200.cu — host side of libswb200.so: the C ABI declared in include/swb200.h.
+//
+// Host orchestration of the alignment hot path (no CPU fallback: every DP cell is computed by the
+// kernels in sw_core.cuh).  What the host does, and the reference code it stands in for:
+//   * tabulate/validate the scoring callback           smithwaterman.cpp:6-38, similaritymatrix.cpp:389-392
+//   * cut the reference into overlapping pieces        plocalaligner.cpp:44-67 (_make_string_range)
+//   * turn every (sequence, piece) into a task, pack tasks two by two into s16x2 "pairs", pick the
+//     lane geometry (L lanes x R rows) and the checkpoint period B, size the HBM work buffers
+//   * launch pass 1 (score), the piece selection of plocalaligner.cpp:122-129, pass 2 (arg-max +
+//     traceback) and, for custom scoring, the default-scoring re-alignment of plocalaligner.cpp:132-136
+#include "../../include/swb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "sw_core.cuh"
+
+using namespace swb;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Geometry { int L = 0, logL = 0, R = 0; };
+const int kRSet[] = {2, 4, 5, 8, 12, 16, 19, 24, 32};
+constexpr int kNumR = sizeof(kRSet) / sizeof(kRSet[0]);
+
+// A launch class: tasks that share lane geometry and block size.
+struct LaunchClass {
+  Geometry geo;
+  std::vector<PairDesc> pairs;
+  std::vector<TaskDesc> tasks;      // task id order: local_read * pieces + piece
+  int pieces = 1;                   // tasks per read (1 = plain SWAligner)
+  int nreads = 0;
+  size_t blk_words = 0, ck_words = 0, q_words = 0;
+  int max_m = 0;
+  // device copies
+  DevBuf d_pairs, d_tasks;
+};
+
+struct HostScoring {
+  int mode = SWB_MODE_SAT_U8;
+  bool match_shaped = true;         // table is a == b ? M : X
+  int M = 3, X = 3, G = 2;          // SAT_U8: saturated; EXACT match-shaped: M = match, X = -mismatch
+  std::vector<int32_t> table;       // EXACT, 256x256, only when !match_shaped
+  int max_pos = 3;                  // largest positive score
+  bool is_default() const { return match_shaped && M == 3 && X == 3 && G == 2; }
+};
+
+}  // namespace
+
+struct swb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  HostScoring sc;
+  // reference
+  std::vector<uint8_t> y;
+  DevBuf d_ref_raw, d_ref_code, d_table;
+  int KP = 0;
+  uint8_t code_of[256];
+  bool table_dirty = true;
+  // staged batch
+  bool staged = false;
+  size_t n_seqs = 0;
+  int npiece = 0;
+  float ratio = 0.f;
+  unsigned flags = 0;
+  size_t cons_stride = 0;
+  int B = 64, logB = 6;
+  std::vector<uint64_t> offsets;
+  std::vector<char> seq_host;       // kept for the custom-scoring re-alignment of the chunked path
+  std::vector<LaunchClass> classes;
+  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_scratch, d_taskmax, d_winner;
+  DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
+  swb_stats stats{};
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+      return SWB_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+int fail(swb_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// _saturate, similaritymatrix.cpp:376-384
+int saturate_u8(float a) { if (a < 0) return 0; if (a > 255) return 255; return (int)(uint8_t)a; }
+
+// Lane geometry for sequences of m rows when `npairs` pairs are in flight.
+bool choose_geometry(int m, size_t npairs, int r_cap, Geometry* out) {
+  struct Cand { int L, R; double eff; double warps; };
+  std::vector<Cand> c;
+  for (int L = 32; L >= 1; L >>= 1) {
+    const int need = (m + L - 1) / L;
+    int R = 0;
+    for (int i = 0; i < kNumR; ++i) if (kRSet[i] >= need && kRSet[i] <= r_cap) { R = kRSet[i]; break; }
+    if (!R) continue;
+    c.push_back({L, R, (double)m / (L * R), (double)npairs * L / 32.0});
+  }
+  if (c.empty()) return false;
+  double best_eff = 0; for (auto& k : c) best_eff = std::max(best_eff, k.eff);
+  const double target = 148.0 * 8.0;
+  const Cand* pick = nullptr;
+  for (auto& k : c) {          // c is ordered by decreasing L: the last admissible candidate has the largest R
+    if (k.eff < best_eff - 0.04) continue;
+    if (!pick) { pick = &k; continue; }
+    if (k.warps >= target) pick = &k;
+  }
+  out->L = pick->L; out->logL = ilog2(pick->L); out->R = pick->R;
+  return true;
+}
+
+Scoring device_scoring(const HostScoring& hs, bool force_default) {
+  int M = force_default ? 3 : hs.M, X = force_default ? 3 : hs.X, G = force_default ? 2 : hs.G;
+  auto pk = [](int v) { return (uint32_t)(uint16_t)(int16_t)v * 0x00010001u; };
+  Scoring s;
+  s.G = G;
+  s.negG2 = pk(-G);
+  const int sm = M + G, sx = G - X;      // (s + G) for match / mismatch
+  s.sel_xor = pk(sx);
+  s.sel_and = pk(sm) ^ pk(sx);
+  s.ceil2 = pk(255 - G);
+  return s;
+}
+
+// ---- kernel dispatch over the compiled (R, SAT, PROFILE) instantiations --------------------------------
+template <int R>
+cudaError_t launch_score_r(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  if (profile) {
+    auto k = sat ? score_kernel<R, true, true> : score_kernel<R, false, true>;
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    k<<<grid, block, smem, st>>>(p);
+  } else {
+    auto k = sat ? score_kernel<R, true, false> : score_kernel<R, false, false>;
+    k<<<grid, block, 0, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+template <int R>
+cudaError_t launch_trace_r(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+  if (profile) {
+    auto k = sat ? trace_kernel<R, true, true> : trace_kernel<R, false, true>;
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    k<<<grid, block, smem, st>>>(p);
+  } else {
+    auto k = sat ? trace_kernel<R, true, false> : trace_kernel<R, false, false>;
+    k<<<grid, block, 0, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_score(int R, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+#define CALL_SCORE(RR) launch_score_r<RR>(sat, profile, grid, block, smem, st, p)
+  switch (R) {
+    case 2: return CALL_SCORE(2); case 4: return CALL_SCORE(4); case 5: return CALL_SCORE(5);
+    case 8: return CALL_SCORE(8); case 12: return CALL_SCORE(12); case 16: return CALL_SCORE(16);
+    case 19: return CALL_SCORE(19); case 24: return CALL_SCORE(24); case 32: return CALL_SCORE(32);
+    default: return cudaErrorInvalidValue;
+  }
+#undef CALL_SCORE
+}
+cudaError_t launch_trace(int R, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+#define CALL_TRACE(RR) launch_trace_r<RR>(sat, profile, grid, block, smem, st, p)
+  switch (R) {
+    case 2: return CALL_TRACE(2); case 4: return CALL_TRACE(4); case 5: return CALL_TRACE(5);
+    case 8: return CALL_TRACE(8); case 12: return CALL_TRACE(12); case 16: return CALL_TRACE(16);
+    case 19: return CALL_TRACE(19); case 24: return CALL_TRACE(24); case 32: return CALL_TRACE(32);
+    default: return cudaErrorInvalidValue;
+  }
+#undef CALL_TRACE
+}
+
+// Upload the (s + G) table of the profile select: [257][KP] int16, row 256 / column KP-1 = sentinels.
+int upload_profile_table(swb_ctx* ctx) {
+  if (!ctx->table_dirty) return SWB_OK;
+  const HostScoring& hs = ctx->sc;
+  if (hs.match_shaped || ctx->y.empty()) { ctx->table_dirty = false; return SWB_OK; }
+  const int KP = ctx->KP;
+  std::vector<int16_t> t((size_t)257 * KP);
+  uint8_t byte_of[256]; memset(byte_of, 0, sizeof byte_of);
+  for (int b = 0; b < 256; ++b) if (ctx->code_of[b] != 0xFF) byte_of[ctx->code_of[b]] = (uint8_t)b;
+  const int16_t never = (int16_t)(-16000);
+  for (int a = 0; a <= 256; ++a)
+    for (int c = 0; c < KP; ++c) {
+      int16_t v = never;
+      if (a < 256 && c < KP - 1) v = (int16_t)(hs.table[(size_t)a * 256 + byte_of[c]] + hs.G);
+      t[(size_t)a * KP + c] = v;
+    }
+  CUDA_TRY(ctx->d_table.ensure(t.size() * sizeof(int16_t)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_table.p, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->table_dirty = false;
+  return SWB_OK;
+}
+
+struct TaskSeed { uint32_t read; uint32_t piece; uint32_t y_off; uint32_t n; uint32_t m; uint32_t x_off; };
+
+// Build launch classes from task seeds (task id = position in `seeds`, grouped by read: pieces contiguous).
+int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, std::vector<LaunchClass>* out) {
+  out->clear();
+  const bool profile = !ctx->sc.match_shaped;
+  int r_cap = 32;
+  if (profile) r_cap = std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128))));
+  // geometry per distinct m
+  std::map<uint32_t, size_t> count_by_m;
+  for (auto& s : seeds) count_by_m[s.m]++;
+  std::map<uint32_t, Geometry> geo_by_m;
+  for (auto& kv : count_by_m) {
+    Geometry g;
+    if (!choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g))
+      return fail(ctx, SWB_ERR_UNSUPPORTED, "sequence of " + std::to_string(kv.first) + " rows exceeds 32 lanes x " + std::to_string(r_cap) + " rows (long-read striping is not built yet)");
+    geo_by_m[kv.first] = g;
+  }
+  std::map<std::pair<int, int>, int> class_of;   // (L, R) -> class index
+  std::vector<int> cls(seeds.size());
+  for (size_t i = 0; i < seeds.size(); i += (size_t)pieces) {
+    const Geometry g = geo_by_m[seeds[i].m];
+    auto key = std::make_pair(g.L, g.R);
+    auto it = class_of.find(key);
+    if (it == class_of.end()) { it = class_of.emplace(key, (int)out->size()).first; out->emplace_back(); out->back().geo = g; out->back().pieces = pieces; }
+    for (int pc = 0; pc < pieces; ++pc) cls[i + pc] = it->second;
+  }
+  // tasks in id order per class; remember ids for pairing
+  std::vector<std::vector<uint32_t>> ids(out->size());
+  for (size_t i = 0; i < seeds.size(); ++i) ids[cls[i]].push_back((uint32_t)i);
+  for (size_t c = 0; c < out->size(); ++c) {
+    LaunchClass& lc = (*out)[c];
+    const int L = lc.geo.L, R = lc.geo.R;
+    auto& id = ids[c];
+    lc.tasks.resize(id.size());
+    lc.nreads = (int)(id.size() / (size_t)pieces);
+    // pairing order: by (y_off, n), then id — tasks of one pair must share the y-range
+    std::vector<uint32_t> order(id.size());
+    std::iota(order.begin(), order.end(), 0u);
+    bool uniform = true;
+    for (size_t k = 1; k < id.size() && uniform; ++k) uniform = seeds[id[k]].y_off == seeds[id[0]].y_off && seeds[id[k]].n == seeds[id[0]].n;
+    if (!uniform)
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const TaskSeed &sa = seeds[id[a]], &sb = seeds[id[b]];
+        if (sa.y_off != sb.y_off) return sa.y_off < sb.y_off;
+        return sa.n < sb.n;
+      });
+    size_t k = 0;
+    while (k < order.size()) {
+      const TaskSeed& a = seeds[id[order[k]]];
+      PairDesc pd{};
+      pd.y_off = a.y_off; pd.n = a.n;
+      pd.nblk = (uint32_t)((a.n + L - 1 + ctx->B - 1) / ctx->B);
+      pd.mA = a.m; pd.xA = a.x_off;
+      const uint32_t pair_idx = (uint32_t)lc.pairs.size();
+      lc.tasks[order[k]] = TaskDesc{pair_idx, 0u, a.read, a.y_off};
+      lc.max_m = std::max(lc.max_m, (int)a.m);
+      if (k + 1 < order.size()) {
+        const TaskSeed& b = seeds[id[order[k + 1]]];
+        if (b.y_off == a.y_off && b.n == a.n) {
+          pd.mB = b.m; pd.xB = b.x_off;
+          lc.tasks[order[k + 1]] = TaskDesc{pair_idx, 1u, b.read, b.y_off};
+          lc.max_m = std::max(lc.max_m, (int)b.m);
+          ++k;
+        }
+      }
+      ++k;
+      pd.q_off = (uint32_t)lc.q_words; lc.q_words += (size_t)L * R;
+      pd.blk_off = lc.blk_words; lc.blk_words += (size_t)pd.nblk * L;
+      pd.ck_off = lc.ck_words; lc.ck_words += (size_t)pd.nblk * (R + 1) * L;
+      lc.pairs.push_back(pd);
+    }
+    if (lc.q_words > 0xFFFFFFFFull) return fail(ctx, SWB_ERR_UNSUPPORTED, "batch too large for one launch class (split the batch)");
+  }
+  return SWB_OK;
+}
+
+int upload_classes(swb_ctx* ctx, std::vector<LaunchClass>& classes) {
+  for (auto& lc : classes) {
+    CUDA_TRY(lc.d_pairs.ensure(lc.pairs.size() * sizeof(PairDesc)));
+    CUDA_TRY(lc.d_tasks.ensure(lc.tasks.size() * sizeof(TaskDesc)));
+    CUDA_TRY(cudaMemcpyAsync(lc.d_pairs.p, lc.pairs.data(), lc.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(lc.d_tasks.p, lc.tasks.data(), lc.tasks.size() * sizeof(TaskDesc), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return SWB_OK;
+}
+
+void free_classes(std::vector<LaunchClass>& classes) {
+  for (auto& lc : classes) { lc.d_pairs.release(); lc.d_tasks.release(); }
+  classes.clear();
+}
+
+// Run pass 1 (+ piece selection) + pass 2 for every class.  `force_default`: plocalaligner.cpp:135 re-alignment.
+int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_default, bool select_pieces, bool trace) {
+  const HostScoring& hs = ctx->sc;
+  const bool sat = hs.mode == SWB_MODE_SAT_U8;
+  const bool profile = !hs.match_shaped && !force_default;
+  for (size_t ci = 0; ci < nclasses; ++ci) {
+    LaunchClass& lc = classes[ci];
+    const int L = lc.geo.L, R = lc.geo.R;
+    CUDA_TRY(ctx->d_qpairs.ensure(lc.q_words * 4));
+    CUDA_TRY(ctx->d_blkmax.ensure(lc.blk_words * 4));
+    CUDA_TRY(ctx->d_ckpt.ensure(lc.ck_words * 4));
+    PassParams pp{};
+    pp.ref_raw = ctx->d_ref_raw.as<uint8_t>();
+    pp.ref_code = ctx->d_ref_code.as<uint8_t>();
+    pp.reads_raw = ctx->d_reads.as<uint8_t>();
+    pp.qpairs = ctx->d_qpairs.as<uint32_t>();
+    pp.table = ctx->d_table.as<int16_t>();
+    pp.KP = ctx->KP;
+    pp.pairs = lc.d_pairs.as<PairDesc>();
+    pp.npairs = (int)lc.pairs.size();
+    pp.blkmax = ctx->d_blkmax.as<uint32_t>();
+    pp.ckpt = ctx->d_ckpt.as<uint32_t>();
+    pp.L = L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
+    pp.sc = device_scoring(hs, force_default);
+    if (profile) pp.sc.G = hs.G;
+
+    // pack rows
+    {
+      const long long total = (long long)lc.pairs.size() * L * R;
+      const int thr = 256;
+      pack_rows_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.reads_raw, pp.pairs, pp.npairs, L * R, ctx->d_qpairs.as<uint32_t>());
+      CUDA_TRY(cudaGetLastError());
+      ctx->stats.kernel_launches++;
+    }
+    // pass 1
+    int warps_per_cta = 4;
+    size_t smem = 0;
+    if (profile) {
+      const size_t per_warp = (size_t)ctx->KP * R * 32 * 4;
+      while (warps_per_cta > 1 && per_warp * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
+      smem = per_warp * warps_per_cta;
+    }
+    const int groups_per_warp = 32 / L;
+    {
+      const size_t warps = (lc.pairs.size() + groups_per_warp - 1) / groups_per_warp;
+      const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
+      CUDA_TRY(launch_score(R, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
+      ctx->stats.kernel_launches++;
+      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nblk * ctx->B * L * R * 2ull;
+    }
+    if (!trace && !select_pieces) continue;
+
+    const uint32_t* task_list = nullptr;
+    int ntrace = (int)lc.tasks.size();
+    if (select_pieces) {
+      CUDA_TRY(ctx->d_taskmax.ensure(lc.tasks.size() * 4));
+      CUDA_TRY(ctx->d_winner.ensure((size_t)lc.nreads * 4));
+      const int thr = 128;
+      task_max_kernel<<<(unsigned)((lc.tasks.size() + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.pairs, lc.d_tasks.as<TaskDesc>(), (int)lc.tasks.size(), pp.blkmax, L, pp.sc.G, ctx->d_taskmax.as<int32_t>());
+      CUDA_TRY(cudaGetLastError());
+      select_piece_kernel<<<(unsigned)((lc.nreads + thr - 1) / thr), thr, 0, ctx->stream>>>(ctx->d_taskmax.as<int32_t>(), lc.nreads, lc.pieces, ctx->d_winner.as<uint32_t>());
+      CUDA_TRY(cudaGetLastError());
+      ctx->stats.kernel_launches += 2;
+      task_list = ctx->d_winner.as<uint32_t>();
+      ntrace = lc.nreads;
+    }
+    if (!trace) continue;
+
+    // pass 2
+    TraceParams tp{};
+    tp.pp = pp;
+    tp.tasks = lc.d_tasks.as<TaskDesc>();
+    tp.task_list = task_list;
+    tp.ntasks = ntrace;
+    tp.mode = hs.mode;
+    int wc = 64; while (wc < L * R + L + 24) wc <<= 1;
+    tp.Wc = wc; tp.rstride = L * R + 1;
+    const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(int16_t);
+    size_t max_groups = (size_t)148 * 16 * groups_per_warp;
+    max_groups = std::min(max_groups, std::max<size_t>(groups_per_warp, ((size_t)2 << 30) / per_group));
+    size_t groups = std::min<size_t>((size_t)ntrace, max_groups);
+    size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
+    const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
+    const size_t total_groups = (size_t)grid * warps_per_cta * groups_per_warp;
+    CUDA_TRY(ctx->d_scratch.ensure(total_groups * per_group));
+    tp.scratch = ctx->d_scratch.as<int16_t>();
+    tp.out_score = ctx->d_score.as<int32_t>();
+    tp.out_pos = ctx->d_pos.as<uint32_t>();
+    tp.out_end = ctx->d_end.as<uint32_t>();
+    tp.out_cx = ctx->d_cx.as<uint8_t>();
+    tp.out_cy = ctx->d_cy.as<uint8_t>();
+    tp.out_len = ctx->d_len.as<uint32_t>();
+    tp.out_flags = ctx->d_flags.as<uint32_t>();
+    tp.cons_cap = (uint32_t)ctx->cons_stride;
+    tp.want_consensus = (ctx->flags & SWB_FLAG_CONSENSUS) ? 1 : 0;
+    if (!tp.want_consensus) tp.cons_cap = 0x7FFFFFFFu;
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(launch_trace(R, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->stats.kernel_launches++;
+    ctx->stats.cells_pass2 += (uint64_t)ntrace * (uint64_t)(3 * ctx->B + lc.max_m + 16) * L * R * 2ull;
+    ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
+  }
+  return SWB_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+const char* swb_version(void) { return "swb200 0.1 (sm_100a)"; }
+
+int swb_create(int device, swb_ctx** out) {
+  if (!out) return SWB_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SWB_ERR_CUDA;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
+  swb_ctx* ctx = new swb_ctx();
+  ctx->device = device;
+  memset(ctx->code_of, 0xFF, sizeof ctx->code_of);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SWB_ERR_CUDA; }
+  for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SWB_ERR_CUDA; }
+  *out = ctx;
+  return SWB_OK;
+}
+
+void swb_destroy(swb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  free_classes(ctx->classes);
+  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt,
+                    &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
+                    &ctx->d_len, &ctx->d_flags}) b->release();
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* swb_last_error(const swb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int swb_set_scoring(swb_ctx* ctx, int mode, const float* table, float gap) {
+  if (!ctx || !table) return SWB_ERR_ARG;
+  if (mode != SWB_MODE_SAT_U8 && mode != SWB_MODE_EXACT) return fail(ctx, SWB_ERR_ARG, "unknown mode");
+  HostScoring hs;
+  hs.mode = mode;
+  if (mode == SWB_MODE_SAT_U8) {
+    // similaritymatrix.cpp:389-392: only two probes of the callback are used
+    hs.M = saturate_u8(table['A' * 256 + 'A']);
+    hs.X = saturate_u8(-table['A' * 256 + 'T']);
+    hs.G = saturate_u8(gap);
+    hs.match_shaped = true;
+    hs.max_pos = hs.M;
+  } else {
+    if (gap != std::floor(gap) || gap < 0 || gap > 4000) return fail(ctx, SWB_ERR_SCORING, "EXACT mode needs an integer gap penalty in [0, 4000]");
+    hs.G = (int)gap;
+    hs.table.resize(65536);
+    int mx = 0;
+    for (int i = 0; i < 65536; ++i) {
+      const float v = table[i];
+      if (v != std::floor(v) || std::fabs(v) > 4000.f) return fail(ctx, SWB_ERR_SCORING, "EXACT mode needs integer-valued scores with |s| <= 4000");
+      hs.table[i] = (int32_t)v;
+      mx = std::max(mx, (int)v);
+    }
+    hs.max_pos = mx;
+    const int32_t d = hs.table[0], o = hs.table[1];
+    bool shaped = true;
+    for (int a = 0; a < 256 && shaped; ++a)
+      for (int b = 0; b < 256; ++b)
+        if (hs.table[a * 256 + b] != (a == b ? d : o)) { shaped = false; break; }
+    hs.match_shaped = shaped;
+    if (shaped) { hs.M = d; hs.X = -o; hs.table.clear(); hs.table.shrink_to_fit(); }
+  }
+  ctx->sc = hs;
+  ctx->table_dirty = true;
+  ctx->staged = false;
+  return SWB_OK;
+}
+
+int swb_set_scoring_match(swb_ctx* ctx, int mode, float match, float mismatch, float gap) {
+  if (!ctx) return SWB_ERR_ARG;
+  std::vector<float> t(65536, mismatch);
+  for (int a = 0; a < 256; ++a) t[a * 256 + a] = match;
+  return swb_set_scoring(ctx, mode, t.data(), gap);
+}
+
+int swb_set_reference(swb_ctx* ctx, const char* y, size_t n) {
+  if (!ctx || (!y && n)) return SWB_ERR_ARG;
+  if (n == 0) return fail(ctx, SWB_ERR_ARG, "empty reference");
+  if (n > 0x7FFF0000ull) return fail(ctx, SWB_ERR_UNSUPPORTED, "reference longer than 2^31");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->y.assign((const uint8_t*)y, (const uint8_t*)y + n);
+  memset(ctx->code_of, 0xFF, sizeof ctx->code_of);
+  int K = 0;
+  std::vector<uint8_t> codes(n);
+  for (size_t i = 0; i < n; ++i) {
+    uint8_t b = ctx->y[i];
+    if (ctx->code_of[b] == 0xFF) ctx->code_of[b] = (uint8_t)K++;
+    codes[i] = ctx->code_of[b];
+  }
+  if (K > 254) { K = 254; }   // profile select is not used with such alphabets (checked at stage time)
+  ctx->KP = K + 1;
+  CUDA_TRY(ctx->d_ref_raw.ensure(n + 64));
+  CUDA_TRY(ctx->d_ref_code.ensure(n + 64));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_ref_raw.p, ctx->y.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_ref_code.p, codes.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->table_dirty = true;
+  ctx->staged = false;
+  return SWB_OK;
+}
+
+int swb_make_string_range(int npiece, int64_t shortlen, int64_t longlen, float ratio, int64_t* left, int64_t* right) {
+  // plocalaligner.cpp:44-67; the three asserts become SWB_ERR_RANGE
+  if (npiece < 1 || !left || !right) return SWB_ERR_RANGE;
+  const int64_t ov = (int64_t)((float)shortlen * ratio);
+  if (npiece == 1) { left[0] = 0; right[0] = longlen; return 1; }
+  const int64_t piece = (longlen + (int64_t)(npiece - 1) * ov) / npiece;
+  if (ov > piece) return SWB_ERR_RANGE;
+  int64_t l = 0, r = piece;
+  int k = 0;
+  left[k] = l; right[k] = r; ++k;
+  while (k < npiece - 1) {
+    l = std::max<int64_t>(0, r - ov);
+    r = std::min(l + piece, longlen);
+    left[k] = l; right[k] = r; ++k;
+  }
+  if (!(r < longlen)) return SWB_ERR_RANGE;
+  left[k] = std::max<int64_t>(0, r - ov); right[k] = longlen; ++k;
+  return k;
+}
+
+int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_seqs, int npiece, float ratio, unsigned flags, size_t cons_stride) {
+  if (!ctx) return SWB_ERR_ARG;
+  if (ctx->y.empty()) return fail(ctx, SWB_ERR_STATE, "swb_set_reference has not been called");
+  if (!seqs || !offsets || n_seqs == 0) return fail(ctx, SWB_ERR_ARG, "empty batch");
+  if ((flags & SWB_FLAG_CONSENSUS) && cons_stride == 0) return fail(ctx, SWB_ERR_ARG, "cons_stride must be > 0 when consensus is requested");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->staged = false;
+  const size_t N = ctx->y.size();
+  const size_t blob = offsets[n_seqs] - offsets[0];
+  if (blob > 0xFFFF0000ull) return fail(ctx, SWB_ERR_UNSUPPORTED, "sequence blob larger than 4 GiB (split the batch)");
+  const HostScoring& hs = ctx->sc;
+  if (!hs.match_shaped && ctx->KP > 200) return fail(ctx, SWB_ERR_UNSUPPORTED, "tabulated scoring needs a reference alphabet of at most 199 symbols");
+
+  ctx->n_seqs = n_seqs; ctx->npiece = npiece; ctx->ratio = ratio; ctx->flags = flags; ctx->cons_stride = cons_stride;
+  ctx->offsets.assign(offsets, offsets + n_seqs + 1);
+  const bool chunked = npiece >= 1;
+  const bool realign = chunked && !hs.is_default();
+  if (realign) ctx->seq_host.assign(seqs + offsets[0], seqs + offsets[n_seqs]); else ctx->seq_host.clear();
+
+  // tasks
+  const int pieces = chunked ? npiece : 1;
+  std::vector<TaskSeed> seeds;
+  seeds.reserve(n_seqs * (size_t)pieces);
+  std::map<uint32_t, std::vector<std::pair<int64_t, int64_t>>> ranges_by_m;
+  uint64_t cells_ref = 0;
+  size_t max_n = 0;
+  uint32_t max_m = 0;
+  for (size_t r = 0; r < n_seqs; ++r) {
+    const uint64_t m64 = offsets[r + 1] - offsets[r];
+    if (m64 == 0) return fail(ctx, SWB_ERR_ARG, "empty sequence at index " + std::to_string(r));
+    const uint32_t m = (uint32_t)m64, xo = (uint32_t)(offsets[r] - offsets[0]);
+    max_m = std::max(max_m, m);
+    cells_ref += (uint64_t)m * N;
+    if (!chunked) { seeds.push_back({(uint32_t)r, 0u, 0u, (uint32_t)N, m, xo}); max_n = N; continue; }
+    auto it = ranges_by_m.find(m);
+    if (it == ranges_by_m.end()) {
+      std::vector<int64_t> l(npiece), rr(npiece);
+      const int k = swb_make_string_range(npiece, m, (int64_t)N, ratio, l.data(), rr.data());
+      if (k < 0) return fail(ctx, SWB_ERR_RANGE, "_make_string_range precondition failed (plocalaligner.cpp:52,63,65) for a sequence of length " + std::to_string(m));
+      std::vector<std::pair<int64_t, int64_t>> v;
+      for (int i = 0; i < k; ++i) v.emplace_back(l[i], rr[i]);
+      it = ranges_by_m.emplace(m, std::move(v)).first;
+    }
+    for (int pc = 0; pc < npiece; ++pc) {
+      const auto& rg = it->second[pc];
+      seeds.push_back({(uint32_t)r, (uint32_t)pc, (uint32_t)rg.first, (uint32_t)(rg.second - rg.first), m, xo});
+      max_n = std::max(max_n, (size_t)(rg.second - rg.first));
+    }
+  }
+  // 16-bit lane range: the largest reachable score must stay below 2^15
+  {
+    const uint64_t reach = (uint64_t)std::min<size_t>(max_m, max_n) * (uint64_t)std::max(1, hs.max_pos) + (uint64_t)hs.G + 16;
+    if (hs.mode == SWB_MODE_EXACT && reach > 32000)
+      return fail(ctx, SWB_ERR_UNSUPPORTED, "EXACT-mode scores may exceed the 16-bit lane range (min(len) * max score = " + std::to_string(reach) + "); the 32-bit path is not built yet");
+  }
+  // checkpoint period: ~256 blocks per range, between 32 and 4096 steps
+  {
+    int B = 32;
+    while (B < 4096 && (size_t)B * 256 < max_n) B <<= 1;
+    ctx->B = B; ctx->logB = ilog2(B);
+  }
+  int rc = upload_profile_table(ctx);
+  if (rc) return rc;
+  free_classes(ctx->classes);
+  rc = build_classes(ctx, seeds, pieces, &ctx->classes);
+  if (rc) return rc;
+  CUDA_TRY(ctx->d_reads.ensure(blob + 64));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_reads.p, seqs + offsets[0], blob, cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_classes(ctx, ctx->classes);
+  if (rc) return rc;
+  // outputs
+  CUDA_TRY(ctx->d_score.ensure(n_seqs * 4));
+  CUDA_TRY(ctx->d_pos.ensure(n_seqs * 4));
+  CUDA_TRY(ctx->d_end.ensure(n_seqs * 8));
+  CUDA_TRY(ctx->d_len.ensure(n_seqs * 4));
+  CUDA_TRY(ctx->d_flags.ensure(n_seqs * 4));
+  if (flags & SWB_FLAG_CONSENSUS) {
+    CUDA_TRY(ctx->d_cx.ensure(n_seqs * cons_stride));
+    CUDA_TRY(ctx->d_cy.ensure(n_seqs * cons_stride));
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->stats = swb_stats{};
+  ctx->stats.cells_reference = cells_ref;
+  ctx->staged = true;
+  return SWB_OK;
+}
+
+int swb_batch_run(swb_ctx* ctx, float* device_us) {
+  if (!ctx) return SWB_ERR_ARG;
+  if (!ctx->staged) return fail(ctx, SWB_ERR_STATE, "no staged batch");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const uint64_t cells_ref = ctx->stats.cells_reference;
+  ctx->stats = swb_stats{};
+  ctx->stats.cells_reference = cells_ref;
+  const bool chunked = ctx->npiece >= 1;
+  const bool realign = chunked && !ctx->sc.is_default();
+  CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (!realign) {
+    int rc = run_classes(ctx, ctx->classes.data(), ctx->classes.size(), false, chunked, true);
+    if (rc) return rc;
+  } else {
+    // custom scoring + chunking: pick the piece with the constructor's scoring (plocalaligner.cpp:113-129),
+    // then re-align the winner with the DEFAULT scoring (plocalaligner.cpp:132-136).
+    std::vector<TaskSeed> winners(ctx->n_seqs);
+    for (size_t c = 0; c < ctx->classes.size(); ++c) {
+      LaunchClass& lc = ctx->classes[c];
+      int rc = run_classes(ctx, &lc, 1, false, true, false);
+      if (rc) return rc;
+      std::vector<uint32_t> win(lc.nreads);
+      CUDA_TRY(cudaMemcpyAsync(win.data(), ctx->d_winner.p, win.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      for (int lr = 0; lr < lc.nreads; ++lr) {
+        const TaskDesc& td = lc.tasks[win[lr]];
+        const PairDesc& pd = lc.pairs[td.pair];
+        winners[td.out] = TaskSeed{td.out, 0u, pd.y_off, pd.n, td.half ? pd.mB : pd.mA, td.half ? pd.xB : pd.xA};
+      }
+    }
+    std::vector<LaunchClass> second;
+    int rc = build_classes(ctx, winners, 1, &second);
+    if (!rc) rc = upload_classes(ctx, second);
+    if (!rc) rc = run_classes(ctx, second.data(), second.size(), true, false, true);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    free_classes(second);
+    if (rc) return rc;
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SWB_ERR_CUDA; }
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0, ms2 = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(&ms2, ctx->ev[2], ctx->ev[3]));
+  const float total_us = ms * 1000.f;
+  ctx->stats.pass2_us = ms2 * 1000.f;
+  ctx->stats.pass1_us = total_us - ctx->stats.pass2_us;
+  if (device_us) *device_us = total_us;
+  return SWB_OK;
+}
+
+int swb_batch_fetch(swb_ctx* ctx, int32_t* score, uint32_t* pos, uint32_t* end_xy, char* cons_x, char* cons_y, uint32_t* cons_len, uint32_t* out_flags) {
+  if (!ctx) return SWB_ERR_ARG;
+  if (!ctx->staged) return fail(ctx, SWB_ERR_STATE, "no staged batch");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n_seqs;
+  if (score) CUDA_TRY(cudaMemcpyAsync(score, ctx->d_score.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pos) CUDA_TRY(cudaMemcpyAsync(pos, ctx->d_pos.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (end_xy) CUDA_TRY(cudaMemcpyAsync(end_xy, ctx->d_end.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cons_len) CUDA_TRY(cudaMemcpyAsync(cons_len, ctx->d_len.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_flags) CUDA_TRY(cudaMemcpyAsync(out_flags, ctx->d_flags.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((ctx->flags & SWB_FLAG_CONSENSUS) && cons_x) CUDA_TRY(cudaMemcpyAsync(cons_x, ctx->d_cx.p, n * ctx->cons_stride, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((ctx->flags & SWB_FLAG_CONSENSUS) && cons_y) CUDA_TRY(cudaMemcpyAsync(cons_y, ctx->d_cy.p, n * ctx->cons_stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return SWB_OK;
+}
+
+int swb_batch_device_results(swb_ctx* ctx, const int32_t** d_score, const uint32_t** d_pos) {
+  if (!ctx || !ctx->staged) return SWB_ERR_STATE;
+  if (d_score) *d_score = ctx->d_score.as<int32_t>();
+  if (d_pos) *d_pos = ctx->d_pos.as<uint32_t>();
+  return SWB_OK;
+}
+
+int swb_align_batch(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_seqs, int npiece, float ratio, unsigned flags,
+                    int32_t* score, uint32_t* pos, uint32_t* end_xy, char* cons_x, char* cons_y, uint32_t* cons_len, size_t cons_stride,
+                    uint32_t* out_flags, float* device_us) {
+  int rc = swb_batch_stage(ctx, seqs, offsets, n_seqs, npiece, ratio, flags, cons_stride);
+  if (rc) return rc;
+  rc = swb_batch_run(ctx, device_us);
+  if (rc) return rc;
+  return swb_batch_fetch(ctx, score, pos, end_xy, cons_x, cons_y, cons_len, out_flags);
+}
+
+int swb_last_stats(const swb_ctx* ctx, swb_stats* out) {
+  if (!ctx || !out) return SWB_ERR_ARG;
+  *out = ctx->stats;
+  return SWB_OK;
+}
+
+int swb_matrix(swb_ctx* ctx, const char* x, size_t m, int32_t* out) {
+  (void)x; (void)m; (void)out;
+  return fail(ctx, SWB_ERR_UNSUPPORTED, "swb_matrix is not built yet");
+}
+
+}  // extern "C"

@@ -64,3 +64,22 @@ def c3_sample():
 def c4_sample():
     with open(os.path.join(GOLDEN, "c4_sample.json")) as f:
         return json.load(f)
+
+
+def load_pkg():
+    """import the hyphen-named product package (parallel-genomeseq_b200)."""
+    import importlib
+    return importlib.import_module("parallel-genomeseq_b200")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return load_pkg()
+
+
+@pytest.fixture(scope="session")
+def engine(pkg):
+    """A swb_ctx on cuda:0.  Fails loudly (no skip, no fallback) when the CUDA path is unavailable."""
+    e = pkg.Engine(0)
+    yield e
+    e.close()
