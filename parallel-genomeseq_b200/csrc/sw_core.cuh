@@ -265,7 +265,7 @@ struct TraceParams {
   const uint32_t* task_list;
   int ntasks;
   int mode;                   // MODE_SAT_U8: skewed raw-order tie-break; MODE_EXACT: column-major
-  int16_t* scratch;           // per group: Wc columns x rstride rows of H
+  uint32_t* scratch;          // per group: Wc columns x rstride rows of packed E words
   int Wc, rstride;            // ring width (power of two), rows per column (L*R + 1)
   int32_t* out_score;
   uint32_t* out_pos;
@@ -294,48 +294,58 @@ __device__ __forceinline__ uint64_t skew_key(int i, int j, int m, int n) {
 }
 __device__ __forceinline__ uint64_t colmajor_key(int i, int j) { return ((uint64_t)(uint32_t)j << 32) | (uint32_t)i; }
 
-template <int R, bool SAT, bool PROFILE>
-struct GroupCtx {
-  const PassParams& p;
-  const PairDesc& pd;
-  CompareSelect<R> csel;
-  ProfileSelect<R> psel;
-  uint32_t gmask;
-  int L, g;
-  __device__ __forceinline__ GroupCtx(const PassParams& p_, const PairDesc& pd_) : p(p_), pd(pd_) {}
-
-  // Restore the wavefront to the start of step t0 + 1 (t0 a multiple of B) and run steps t0+1 .. t1.
-  template <class Hook>
-  __device__ __forceinline__ void run(LaneState<R>& st, int t0, int t1, Hook&& hook) {
-    if (t0 == 0) init_state<R>(st, p.sc);
-    else load_state<R>(st, p.ckpt + pd.ck_off + (size_t)((t0 >> p.logB) - 1) * (R + 1) * L, L, g);
-    uint32_t bmax = NEG_INF2;
-    uint32_t ynext = load_y<PROFILE>(p, pd, t0 + 1 - g);
-    for (int t = t0 + 1; t <= t1; ++t) {
-      const uint32_t ycur = ynext;
-      ynext = load_y<PROFILE>(p, pd, t + 1 - g);
-      uint32_t up_cur = __shfl_up_sync(gmask, st.E[R - 1], 1, L);
-      if (g == 0) up_cur = p.sc.negG2;
-      const int j = t - g;
-      auto h = [&](int k, uint32_t e_new, uint32_t, uint32_t, uint32_t) { hook(k, j, e_new); };
-      if (PROFILE) { psel.set_column(ycur); step<R, SAT>(st, psel, p.sc, up_cur, bmax, h); }
-      else { csel.set_column(ycur); step<R, SAT>(st, csel, p.sc, up_cur, bmax, h); }
-    }
-  }
-};
-
-__device__ __forceinline__ uint64_t group_min_u64(uint64_t v, uint32_t gmask, int L) {
+__device__ __forceinline__ uint64_t group_min_u64(uint64_t v, int L) {
   for (int o = L >> 1; o > 0; o >>= 1) {
-    uint32_t lo = __shfl_xor_sync(gmask, (uint32_t)v, o), hi = __shfl_xor_sync(gmask, (uint32_t)(v >> 32), o);
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
     uint64_t w = ((uint64_t)hi << 32) | lo;
     v = w < v ? w : v;
   }
   return v;
 }
-__device__ __forceinline__ int group_max_i32(int v, uint32_t gmask, int L) {
-  for (int o = L >> 1; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
+__device__ __forceinline__ int group_max_i32(int v, int L) {
+  for (int o = L >> 1; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ int warp_max_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Pass 2 runs the 32/L groups of a warp in LOCKSTEP: every group owns one task, all groups execute the
+// same instruction stream (restore a checkpoint, run some wavefront steps, feed a per-cell hook) and only
+// the hook is predicated per group.  The cost of a round is the longest group's, not the sum.
+template <int R, bool SAT, bool PROFILE>
+struct Replay {
+  const PassParams& p;
+  CompareSelect<R> csel;
+  ProfileSelect<R> psel;
+  LaneState<R> st;
+  int L, g;
+  __device__ __forceinline__ Replay(const PassParams& p_) : p(p_) {}
+
+  // Run `nsteps` steps (warp-uniform) starting after step t0 (per group, a multiple of B); hook(k, j, e_new)
+  // is called for steps t <= t1 (per group) only.
+  template <class Hook>
+  __device__ __forceinline__ void run(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
+    if (t0 == 0) init_state<R>(st, p.sc);
+    else load_state<R>(st, p.ckpt + pd.ck_off + (size_t)((t0 >> p.logB) - 1) * (R + 1) * L, L, g);
+    uint32_t bmax = NEG_INF2;
+    uint32_t ynext = load_y<PROFILE>(p, pd, t0 + 1 - g);
+    for (int s = 1; s <= nsteps; ++s) {
+      const int t = t0 + s;
+      const uint32_t ycur = ynext;
+      ynext = load_y<PROFILE>(p, pd, t + 1 - g);
+      uint32_t up_cur = __shfl_up_sync(0xffffffffu, st.E[R - 1], 1, L);
+      if (g == 0) up_cur = p.sc.negG2;
+      const int j = t - g;
+      const bool on = t <= t1;
+      auto h = [&](int k, uint32_t e_new, uint32_t, uint32_t, uint32_t) { if (on) hook(k, j, e_new); };
+      if (PROFILE) { psel.set_column(ycur); step<R, SAT>(st, psel, p.sc, up_cur, bmax, h); }
+      else { csel.set_column(ycur); step<R, SAT>(st, csel, p.sc, up_cur, bmax, h); }
+    }
+  }
+};
 
 template <int R, bool SAT, bool PROFILE>
 __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
@@ -347,14 +357,23 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
   const int g = lane & (L - 1);
   const int grp_in_warp = lane >> p.logL;
   const int groups_per_warp = 32 >> p.logL;
-  const uint32_t gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp_in_warp * L));
-  const int ggroup = (blockIdx.x * (blockDim.x >> 5) + warp_in_cta) * groups_per_warp + grp_in_warp;
-  const int ngroups = gridDim.x * (blockDim.x >> 5) * groups_per_warp;
-  int16_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int ggroup = gwarp * groups_per_warp + grp_in_warp;
+  uint32_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;
+  const int wmask = tp.Wc - 1;
   const int G = p.sc.G;
+  const int row0 = g * R + 1;          // first H row of this lane
+  const uint32_t gshift = (uint32_t)(grp_in_warp * L);
+  const uint32_t gbits = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
 
-  for (int ti = ggroup; ti < tp.ntasks; ti += ngroups) {
-    const TaskDesc td = tp.tasks[tp.task_list ? tp.task_list[ti] : ti];
+  Replay<R, SAT, PROFILE> rp(p);
+  rp.L = L; rp.g = g;
+
+  for (int base = gwarp * groups_per_warp; base < tp.ntasks; base += nwarps * groups_per_warp) {   // warp-uniform
+    const int ti = base + grp_in_warp;
+    bool active = ti < tp.ntasks;
+    const TaskDesc td = tp.tasks[tp.task_list ? tp.task_list[active ? ti : base] : (active ? ti : base)];
     const PairDesc pd = p.pairs[td.pair];
     const int m = td.half ? pd.mB : pd.mA;
     const int n = pd.n;
@@ -362,134 +381,145 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     const uint8_t* xraw = p.reads_raw + (td.half ? pd.xB : pd.xA);
     const uint8_t* yraw = p.ref_raw + pd.y_off;
 
-    GroupCtx<R, SAT, PROFILE> gc(p, pd);
-    gc.gmask = gmask; gc.L = L; gc.g = g;
     if (PROFILE) {
-      // one profile slice per warp: groups of a warp may hold different pairs, each lane fills its own slice
       uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
-      __syncwarp(gmask);
-      build_profile<R>(prof_warp, p, pd, g, lane);
-      gc.psel.prof = prof_warp + lane;
-      __syncwarp(gmask);
+      build_profile<R>(prof_warp, p, pd, g, lane);     // every lane fills (and later reads) only its own column
+      rp.psel.prof = prof_warp + lane;
     } else {
-      load_compare_rows<R>(gc.csel, p, pd, g);
+      load_compare_rows<R>(rp.csel, p, pd, g);
     }
 
-    // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------
+    // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------------
     const uint32_t* blk = p.blkmax + pd.blk_off;
     int vmax = -32768;
     for (uint32_t w = g; w < pd.nblk * (uint32_t)L; w += L) vmax = max(vmax, half_of(blk[w], half));
-    vmax = group_max_i32(vmax, gmask, L);
+    vmax = group_max_i32(vmax, L);
     const int score = vmax + G;
-    if (m == 0 || score <= 0) {
+    if (active && (m == 0 || score <= 0)) {
       // all-zero matrix: the reference reads H(-1,-1) (undefined); we return score 0, pos 0, "".
       if (g == 0) {
         tp.out_score[td.out] = 0; tp.out_pos[td.out] = 0; tp.out_len[td.out] = 0;
         tp.out_end[2 * td.out] = 0; tp.out_end[2 * td.out + 1] = 0; tp.out_flags[td.out] = 0;
       }
-      continue;
+      active = false;
     }
 
-    // ---- 2. arg-max with the reference's tie-break ----------------------------------------------------
-    // candidate blocks: some lane's block maximum equals vmax.  Cells equal to the maximum are recomputed
-    // and keyed; the smallest key wins (skewed raw order for SAT_U8, column-major for EXACT).
+    // ---- 2. arg-max with the reference's tie-break --------------------------------------------------------
+    // Candidate blocks: some lane's block maximum equals vmax.  Their cells are recomputed and keyed; the
+    // smallest key wins (skewed raw order for SAT_U8, column-major for EXACT).  Blocks whose smallest
+    // possible key already exceeds the current winner are skipped.
     const int ncols_raw = max(n + 1, m + 1);
     uint64_t best = ~0ull;
-    LaneState<R> st;
-    const int row0 = g * R + 1;          // first H row of this lane
-    auto scan_block = [&](int b) {
-      const int t0 = b << p.logB;
-      const int jmin = max(1, t0 + 1 - (L - 1)), jmax = min(n, t0 + p.B);
-      if (jmin > jmax) return;
-      uint64_t lb;
-      if (tp.mode == MODE_SAT_U8) lb = (jmax + m >= ncols_raw) ? 0ull : ((uint64_t)(uint32_t)(jmin + 1) << 32);
-      else lb = (uint64_t)(uint32_t)jmin << 32;
-      if (lb > best) return;             // every key in this block is larger than the current winner
-      uint64_t mine = ~0ull;
-      gc.run(st, t0, t0 + p.B, [&](int k, int j, uint32_t e_new) {
-        const int i = row0 + k;
-        if (half_of(e_new, half) == vmax && i <= m && j >= 1 && j <= n) {
-          const uint64_t key = (tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j);
-          mine = key < mine ? key : mine;
-        }
-      });
-      mine = group_min_u64(mine, gmask, L);
-      best = mine < best ? mine : best;
-    };
-    // blocks that may hold wrapped (lower-triangle) cells sort first in the skewed order: visit them first
-    int b_wrap = (int)pd.nblk;
+    int b_wrap = (int)pd.nblk;           // blocks >= b_wrap may hold wrapped (lower-triangle) cells: visited first
     if (tp.mode == MODE_SAT_U8) {
-      const int need = ncols_raw - m;                        // jmax >= need  <=> block may wrap
+      const int need = ncols_raw - m;
       b_wrap = max(0, ((need + p.B - 1) >> p.logB) - 1);
       if (b_wrap > (int)pd.nblk) b_wrap = (int)pd.nblk;
     }
-    for (int pass = 0; pass < 2; ++pass) {
-      const int b_lo = pass == 0 ? b_wrap : 0, b_hi = pass == 0 ? (int)pd.nblk : b_wrap;
-      for (int bb = b_lo; bb < b_hi; bb += L) {
-        const int b = bb + g;
+    int cursor = active ? 0 : 2 * (int)pd.nblk;     // positions 0..nblk-b_wrap-1 -> wrapped part, then the rest
+    const int n_first = (int)pd.nblk - b_wrap;
+    const uint32_t vmax2 = (uint32_t)(uint16_t)(int16_t)vmax * 0x00010001u;
+    const uint32_t hmask = half ? 0xFFFF0000u : 0x0000FFFFu;
+    while (true) {
+      // each group advances its cursor to its next admissible candidate block (L blocks per probe)
+      int myb = -1;
+      while (true) {                                   // warp-uniform loop; the body is predicated per group
+        const bool searching = cursor < (int)pd.nblk && myb < 0;
+        if (!__any_sync(0xffffffffu, searching)) break;
+        const int pos = cursor + g;
         bool cand = false;
-        if (b < b_hi) {
+        int b = -1;
+        if (searching && pos < (int)pd.nblk) {
+          b = pos < n_first ? b_wrap + pos : pos - n_first;
           int bm = -32768;
           for (int q = 0; q < L; ++q) bm = max(bm, half_of(blk[(size_t)b * L + q], half));
-          cand = (bm == vmax);
+          if (bm == vmax) {
+            const int t0 = b << p.logB;
+            const int jmin = max(1, t0 + 1 - (L - 1)), jmax = min(n, t0 + p.B);
+            if (jmin <= jmax) {
+              uint64_t lb;
+              if (tp.mode == MODE_SAT_U8) lb = (jmax + m >= ncols_raw) ? 0ull : ((uint64_t)(uint32_t)(jmin + 1) << 32);
+              else lb = (uint64_t)(uint32_t)jmin << 32;
+              cand = lb <= best;
+            }
+          }
         }
-        uint32_t cm = (__ballot_sync(gmask, cand) & gmask) >> (grp_in_warp * L);
-        while (cm) { const int q = __ffs(cm) - 1; cm &= cm - 1; scan_block(bb + q); }
+        const uint32_t cm = (__ballot_sync(0xffffffffu, cand) >> gshift) & gbits;
+        const int q = cm ? __ffs(cm) - 1 : 0;
+        const int bsel = __shfl_sync(0xffffffffu, b, (int)gshift + q);
+        if (searching) {
+          if (cm) { myb = bsel; cursor += q + 1; } else { cursor += L; }
+        }
+      }
+      if (!__any_sync(0xffffffffu, myb >= 0)) break;
+      const bool has = myb >= 0;
+      const int t0 = has ? (myb << p.logB) : 0;
+      uint64_t mine = ~0ull;
+      rp.run(pd, t0, has ? t0 + p.B : -1, p.B, [&](int k, int j, uint32_t e_new) {
+        if (((e_new ^ vmax2) & hmask) == 0) {
+          const int i = row0 + k;
+          if (i <= m && j >= 1 && j <= n) {
+            const uint64_t key = (tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j);
+            mine = key < mine ? key : mine;
+          }
+        }
+      });
+      mine = group_min_u64(mine, L);
+      best = mine < best ? mine : best;
+    }
+    int ie = 1, je = 1;
+    if (active) {
+      if (tp.mode == MODE_SAT_U8) {
+        // invert skew_key: _rawindex2trueindex, similaritymatrix.cpp:330-346
+        const int rj = (int)(best >> 32), ri = (int)(uint32_t)best;
+        const int len_x = n + 1, len_y = m + 1, nrows = min(len_x, len_y);
+        int t_i, t_j;
+        if (rj < nrows - 1) {
+          if (ri <= rj) { t_i = ri; t_j = rj - ri; } else { t_i = len_x - nrows + ri; t_j = len_y - ri + rj; }
+        } else {
+          if (len_x <= len_y) { t_i = ri; t_j = rj - ri; } else { t_i = rj - (nrows - 1) + ri; t_j = nrows - 1 - ri; }
+        }
+        je = t_i; ie = t_j;
+      } else { je = (int)(best >> 32); ie = (int)(uint32_t)best; }
+      if (g == 0) {
+        tp.out_score[td.out] = score;
+        tp.out_end[2 * td.out] = (uint32_t)ie; tp.out_end[2 * td.out + 1] = (uint32_t)je;
       }
     }
-    int ie, je;
-    if (tp.mode == MODE_SAT_U8) {
-      // invert skew_key: _rawindex2trueindex, similaritymatrix.cpp:330-346
-      const int rj = (int)(best >> 32), ri = (int)(uint32_t)best;
-      const int len_x = n + 1, len_y = m + 1, nrows = min(len_x, len_y);
-      int t_i, t_j;
-      if (rj < nrows - 1) {
-        if (ri <= rj) { t_i = ri; t_j = rj - ri; } else { t_i = len_x - nrows + ri; t_j = len_y - ri + rj; }
-      } else {
-        if (len_x <= len_y) { t_i = ri; t_j = rj - ri; } else { t_i = rj - (nrows - 1) + ri; t_j = nrows - 1 - ri; }
-      }
-      je = t_i; ie = t_j;
-    } else { je = (int)(best >> 32); ie = (int)(uint32_t)best; }
 
-    if (g == 0) {
-      tp.out_score[td.out] = score;
-      tp.out_end[2 * td.out] = (uint32_t)ie; tp.out_end[2 * td.out + 1] = (uint32_t)je;
-    }
-
-    // ---- 3. traceback over a ring of recomputed columns ---------------------------------------------
+    // ---- 3. traceback over a ring of recomputed columns ---------------------------------------------------
     // SWAligner::traceback, smithwaterman.cpp:40-78, literally: compare the three neighbours' VALUES.
     int ix = ie, iy = je;
     uint32_t len = 0, flags = 0, pos = 0;
     uint8_t* cx = tp.out_cx + (size_t)td.out * tp.cons_cap;
     uint8_t* cy = tp.out_cy + (size_t)td.out * tp.cons_cap;
-    const int wmask = tp.Wc - 1;
-    bool done = false;
-    while (!done) {
+    bool done = !active;
+    while (!__all_sync(0xffffffffu, done)) {
       const int l_e = (ix - 1) / R;
-      const int t_hi = iy + l_e;
-      // restart point: a checkpoint at or before column iy - 2 - lookback (lookback: the rows still above us)
-      int c_lo = iy - 2 - (ix + 8);
+      const int t_hi = done ? 0 : iy + l_e;
+      int c_lo = iy - 2 - (ix + 8);      // restart at a checkpoint left of the columns the remaining rows can reach
       if (c_lo < 0) c_lo = 0;
-      const int t_lo = (c_lo >> p.logB) << p.logB;
+      const int t_lo = done ? 0 : ((c_lo >> p.logB) << p.logB);
       const int valid_lo = max(t_lo, t_hi - tp.Wc + 1);     // oldest column every lane still holds
-      if (t_lo > 0) {
+      if (!done && t_lo > 0) {
         // the checkpoint itself is column t_lo - g of this lane's rows
-        LaneState<R> ck; load_state<R>(ck, p.ckpt + pd.ck_off + (size_t)((t_lo >> p.logB) - 1) * (R + 1) * L, L, g);
+        const uint32_t* ck = p.ckpt + pd.ck_off + (size_t)((t_lo >> p.logB) - 1) * (R + 1) * L;
         const int jc = t_lo - g;
         if (jc >= 0) {
 #pragma unroll
-          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + row0 + k] = (int16_t)(half_of(ck.E[k], half) + G);
+          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + row0 + k] = ck[k * L + g];
         }
       }
-      gc.run(st, t_lo, t_hi, [&](int k, int j, uint32_t e_new) {
-        if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + row0 + k] = (int16_t)(half_of(e_new, half) + G);
+      const int nsteps = warp_max_i32(t_hi - t_lo);
+      rp.run(pd, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
+        if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + row0 + k] = e_new;
       });
-      __syncwarp(gmask);
-      if (g == 0) {
-        // row 0 and column 0 of H are zero and never stored
+      __syncwarp();
+      if (g == 0 && !done) {
+        // row 0 and column 0 of H are zero and never stored; stored words are packed E = H - G
         auto Hat = [&](int i, int j) -> int {
           if (i <= 0 || j <= 0) return 0;
-          return (int)((volatile int16_t*)scr)[(size_t)(j & wmask) * tp.rstride + i];
+          return half_of(((volatile uint32_t*)scr)[(size_t)(j & wmask) * tp.rstride + i], half) + G;
         };
         while (true) {
           if (iy - 1 < valid_lo && iy - 1 > 0) break;        // window exhausted: recompute further left
@@ -504,17 +534,16 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
           else { if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = '-'; } --ix; }
           ++len;
         }
+        if (done) {
+          tp.out_pos[td.out] = pos + td.pos_add;
+          tp.out_len[td.out] = len;
+          tp.out_flags[td.out] = flags;
+        }
       }
-      // broadcast the walker's state to the group
-      const int src = grp_in_warp * L;
-      ix = __shfl_sync(gmask, ix, src); iy = __shfl_sync(gmask, iy, src);
-      done = __shfl_sync(gmask, (int)done, src) != 0;
-      __syncwarp(gmask);
-    }
-    if (g == 0) {
-      tp.out_pos[td.out] = pos + td.pos_add;
-      tp.out_len[td.out] = len;
-      tp.out_flags[td.out] = flags;
+      __syncwarp();
+      // broadcast the walker's state to its group
+      ix = __shfl_sync(0xffffffffu, ix, (int)gshift); iy = __shfl_sync(0xffffffffu, iy, (int)gshift);
+      done = __shfl_sync(0xffffffffu, (int)done, (int)gshift) != 0;
     }
   }
 }

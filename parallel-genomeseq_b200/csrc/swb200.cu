@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -389,7 +390,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.mode = hs.mode;
     int wc = 64; while (wc < L * R + L + 24) wc <<= 1;
     tp.Wc = wc; tp.rstride = L * R + 1;
-    const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(int16_t);
+    const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(uint32_t);
     size_t max_groups = (size_t)148 * 16 * groups_per_warp;
     max_groups = std::min(max_groups, std::max<size_t>(groups_per_warp, ((size_t)2 << 30) / per_group));
     size_t groups = std::min<size_t>((size_t)ntrace, max_groups);
@@ -397,7 +398,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
     const size_t total_groups = (size_t)grid * warps_per_cta * groups_per_warp;
     CUDA_TRY(ctx->d_scratch.ensure(total_groups * per_group));
-    tp.scratch = ctx->d_scratch.as<int16_t>();
+    tp.scratch = ctx->d_scratch.as<uint32_t>();
     tp.out_score = ctx->d_score.as<int32_t>();
     tp.out_pos = ctx->d_pos.as<uint32_t>();
     tp.out_end = ctx->d_end.as<uint32_t>();
@@ -600,10 +601,14 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     if (hs.mode == SWB_MODE_EXACT && reach > 32000)
       return fail(ctx, SWB_ERR_UNSUPPORTED, "EXACT-mode scores may exceed the 16-bit lane range (min(len) * max score = " + std::to_string(reach) + "); the 32-bit path is not built yet");
   }
-  // checkpoint period: ~256 blocks per range, between 32 and 4096 steps
+  // checkpoint period B (steps between register-state checkpoints): as small as the HBM budget for the
+  // checkpoints allows (pass 2 recomputes O(B) columns per alignment), at least 32.
   {
+    size_t budget_mb = 8192;
+    if (const char* e = getenv("SWB_CKPT_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
+    const double words_per_block = (double)((seeds.size() + 1) / 2) * ((double)max_m * 1.08 + 40.0);
     int B = 32;
-    while (B < 4096 && (size_t)B * 256 < max_n) B <<= 1;
+    while (B < 65536 && words_per_block * 4.0 * ((double)max_n / B + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
     ctx->B = B; ctx->logB = ilog2(B);
   }
   int rc = upload_profile_table(ctx);
