@@ -169,6 +169,7 @@ def main():
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("parallel-genomeseq_b200")
+    sharding = importlib.import_module("parallel-genomeseq_b200.sharding")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -204,11 +205,8 @@ def main():
         s = torch.as_tensor(cuda_array(ds, n_reads, "<i4"), device="cuda")
         p = torch.as_tensor(cuda_array(dp, n_reads, "<u4"), device="cuda").view(torch.int32)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        out_s = torch.empty(world * n_reads, dtype=torch.int32, device="cuda")
-        out_p = torch.empty(world * n_reads, dtype=torch.int32, device="cuda")
         e0.record()
-        dist.all_gather_into_tensor(out_s, s)
-        dist.all_gather_into_tensor(out_p, p)
+        sharding.gather_score_pos(s, p)
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1) * 1e3

@@ -110,6 +110,10 @@ namespace {
 
 int fail(swb_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
 
+// Symbol-score selection of the kernels: "profile" = per-warp query profile in shared memory (one LDS per
+// cell pair, any scoring table), "compare" = HSET2 + LOP3 on packed symbols (match/mismatch scoring only).
+bool use_profile(const swb_ctx* ctx, bool force_default);
+
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // _saturate, similaritymatrix.cpp:376-384
@@ -137,6 +141,14 @@ bool choose_geometry(int m, size_t npairs, int r_cap, Geometry* out) {
   }
   out->L = pick->L; out->logL = ilog2(pick->L); out->R = pick->R;
   return true;
+}
+
+bool use_profile(const swb_ctx* ctx, bool force_default) {
+  const HostScoring& hs = ctx->sc;
+  if (!hs.match_shaped && !force_default) return true;
+  if (force_default && !hs.is_default()) return false;      // the profile table holds the constructor's scoring
+  if (const char* e = getenv("SWB_SELECT")) { if (!strcmp(e, "profile")) return ctx->KP <= 64; if (!strcmp(e, "compare")) return false; }
+  return false;
 }
 
 Scoring device_scoring(const HostScoring& hs, bool force_default) {
@@ -202,7 +214,7 @@ cudaError_t launch_trace(int R, bool sat, bool profile, dim3 grid, dim3 block, s
 int upload_profile_table(swb_ctx* ctx) {
   if (!ctx->table_dirty) return SWB_OK;
   const HostScoring& hs = ctx->sc;
-  if (hs.match_shaped || ctx->y.empty()) { ctx->table_dirty = false; return SWB_OK; }
+  if (ctx->y.empty()) { ctx->table_dirty = false; return SWB_OK; }
   const int KP = ctx->KP;
   std::vector<int16_t> t((size_t)257 * KP);
   uint8_t byte_of[256]; memset(byte_of, 0, sizeof byte_of);
@@ -211,7 +223,10 @@ int upload_profile_table(swb_ctx* ctx) {
   for (int a = 0; a <= 256; ++a)
     for (int c = 0; c < KP; ++c) {
       int16_t v = never;
-      if (a < 256 && c < KP - 1) v = (int16_t)(hs.table[(size_t)a * 256 + byte_of[c]] + hs.G);
+      if (a < 256 && c < KP - 1) {
+        const int sc = hs.match_shaped ? (a == byte_of[c] ? hs.M : -hs.X) : hs.table[(size_t)a * 256 + byte_of[c]];
+        v = (int16_t)(sc + hs.G);
+      }
       t[(size_t)a * KP + c] = v;
     }
   CUDA_TRY(ctx->d_table.ensure(t.size() * sizeof(int16_t)));
@@ -226,7 +241,7 @@ struct TaskSeed { uint32_t read; uint32_t piece; uint32_t y_off; uint32_t n; uin
 // Build launch classes from task seeds (task id = position in `seeds`, grouped by read: pieces contiguous).
 int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, std::vector<LaunchClass>* out) {
   out->clear();
-  const bool profile = !ctx->sc.match_shaped;
+  const bool profile = use_profile(ctx, false);
   int r_cap = 32;
   if (profile) r_cap = std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128))));
   // geometry per distinct m
@@ -317,7 +332,7 @@ void free_classes(std::vector<LaunchClass>& classes) {
 int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_default, bool select_pieces, bool trace) {
   const HostScoring& hs = ctx->sc;
   const bool sat = hs.mode == SWB_MODE_SAT_U8;
-  const bool profile = !hs.match_shaped && !force_default;
+  const bool profile = use_profile(ctx, force_default);
   for (size_t ci = 0; ci < nclasses; ++ci) {
     LaunchClass& lc = classes[ci];
     const int L = lc.geo.L, R = lc.geo.R;

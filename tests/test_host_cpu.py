@@ -1,0 +1,136 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/swb200.h declares,
+host-only entry points behave like the reference, the product refuses to run without a CUDA device,
+and the N>1 sharding + gather logic works over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import pyoracle as o
+from conftest import ROOT, load_pkg
+
+
+def test_library_exports_every_declared_symbol():
+    pkg = load_pkg()
+    lib = pkg.load_library()
+    with open(os.path.join(ROOT, "include", "swb200.h")) as f:
+        hdr = f.read()
+    declared = sorted(set(re.findall(r"\b(swb_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(pkg.EXPORTS) == declared
+    assert b"sm_100a" in lib.swb_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    pkg = load_pkg()
+    with pytest.raises(pkg.SwbError) as ei:
+        pkg.Engine(0)
+    assert ei.value.code == -1
+
+
+def test_product_never_touches_the_oracle():
+    """The product package must not import, load or name anything under oracle/."""
+    pdir = os.path.join(ROOT, "parallel-genomeseq_b200")
+    for root, _, files in os.walk(pdir):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                with open(os.path.join(root, fn), errors="ignore") as f:
+                    txt = f.read()
+                assert "pyoracle" not in txt and "sw_oracle" not in txt and "liboracle" not in txt and "libref_aligner" not in txt, fn
+
+
+def test_make_string_range_matches_oracle_and_reference_values():
+    """swb_make_string_range == _make_string_range (plocalaligner.cpp:44-67), incl. the assert preconditions."""
+    pkg = load_pkg()
+    assert pkg.make_string_range(4, 125, 4980, 2.0) == [(0, 1432), (1182, 2614), (2364, 3796), (3546, 4980)]
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        npiece = int(rng.integers(1, 20)); m = int(rng.integers(1, 400)); n = int(rng.integers(1, 20000)); ratio = float(rng.choice([0.5, 1.0, 1.5, 2.0, 2.5]))
+        want = o.make_string_range(npiece, m, n, ratio)
+        if isinstance(want, int):
+            with pytest.raises(pkg.SwbError):
+                pkg.make_string_range(npiece, m, n, ratio)
+        else:
+            assert pkg.make_string_range(npiece, m, n, ratio) == want
+
+
+def test_pack_sequences():
+    pkg = load_pkg()
+    blob, offs = pkg.pack_sequences(["ACG", "T", "GGCA"])
+    assert blob.tobytes() == b"ACGTGGCA" and offs.tolist() == [0, 3, 4, 8]
+    arr = np.frombuffer(b"ACGTACGT", dtype=np.uint8).reshape(2, 4)
+    blob, offs = pkg.pack_sequences(arr)
+    assert offs.tolist() == [0, 4, 8]
+
+
+def test_block_partition_like_mpi_driver():
+    pkg = load_pkg()
+    import importlib
+    sh = importlib.import_module("parallel-genomeseq_b200.sharding")
+    assert sh.block_partition(1170, 8) == [(i * 146, (i + 1) * 146) for i in range(7)] + [(1022, 1170)]
+    assert sh.block_partition(10, 1) == [(0, 10)]
+    parts = sh.block_partition(1_000_000, 8)
+    assert parts[0] == (0, 125000) and parts[-1] == (875000, 1000000)
+
+
+def test_synth_workloads_are_seeded():
+    pkg = load_pkg()
+    a, b = pkg.synth.c3_reference(5000), pkg.synth.c3_reference(5000)
+    assert a == b and set(a) <= set("ACGT")
+    r = pkg.synth.c3_reads(a, 5, read_len=150)
+    assert all(len(x) == 150 for x in r)
+    t = pkg.synth.blosum62_table()
+    assert t[ord("W"), ord("W")] == 11 and t[ord("A"), ord("R")] == -1 and (t == t.T).all()
+
+
+_WORKER = r'''
+import importlib, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=rank, world_size=world)
+sh = importlib.import_module("parallel-genomeseq_b200.sharding")
+n = 1171
+parts = sh.block_partition(n, world)
+lo, hi = parts[rank]
+score = torch.arange(lo, hi, dtype=torch.int32) * 3 + 1       # stand-in for this rank's kernel results
+pos = torch.arange(lo, hi, dtype=torch.int32) + 7
+s_all, p_all = sh.gather_score_pos(score, pos, counts=[b - a for a, b in parts])
+assert s_all.tolist() == [3 * i + 1 for i in range(n)], rank
+assert p_all.tolist() == [i + 7 for i in range(n)], rank
+e_s, e_p = sh.gather_score_pos(score[:500].contiguous(), pos[:500].contiguous())
+assert e_s.numel() == 500 * world and e_s[500].item() == 3 * parts[1][0] + 1
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # bench.py: max-over-ranks time
+assert t.item() == world
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharding_and_gather_world_size_2_gloo(tmp_path):
+    """The N>1 path of bench.py on CPU: block partition, ragged all-gather, max-over-ranks, world_size 2, gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + (os.getpid() % 2000))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, port], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out
+        assert f"rank {r} ok" in out
