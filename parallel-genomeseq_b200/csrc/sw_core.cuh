@@ -37,11 +37,11 @@ struct PairDesc {
   uint32_t q_off;     // word offset into qpairs: L*R packed rows
   uint32_t y_off;     // first y position of this pair's range (0-based)
   uint32_t n;         // columns in the range
-  uint32_t nblk;      // ceil((n + L) / B) blocks of B steps
+  uint32_t nblk;      // ceil((L - 1 + ceil(n / C)) / B) blocks of B steps
   uint32_t mA, mB;    // real row counts (0 = empty half)
   uint32_t xA, xB;    // byte offsets of the raw sequences in reads_raw
   uint64_t blk_off;   // word offset into blkmax: nblk * L words
-  uint64_t ck_off;    // word offset into ckpt  : nblk * (R+1) * L words
+  uint64_t ck_off;    // word offset into ckpt  : nblk * (R+C) * L words
 };
 
 struct Scoring {
@@ -83,57 +83,83 @@ constexpr uint32_t SYM_BASE = 0x4000u;
 constexpr uint32_t SENT_Y = SYM_BASE | 0x0100u;   // never equals a byte symbol
 constexpr uint32_t SENT_X = SYM_BASE | 0x0101u;   // never equals a byte symbol nor SENT_Y
 
-// Per-lane register state of the wavefront for one pair.
-template <int R>
-struct LaneState {
-  uint32_t E[R];      // H - G of this lane's R rows at the previous column
-  uint32_t up_prev;   // H - G of the row above this lane's first row at the previous column
-};
+__device__ __forceinline__ int warp_max_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 
-// Symbol selection: returns pack(s+G) for row k against the current column.
-template <int R>
+// Per-lane register state of the wavefront for one pair.  A step advances every lane by C columns.
+template <int R, int C>
+struct LaneState {
+  uint32_t E[R];        // H - G of this lane's R rows at the last column of the previous step
+  uint32_t up_prev;     // H - G of the row above this lane's first row at that same column
+  uint32_t bot[C];      // H - G of this lane's LAST row at each of the C columns of the previous step
+                        // (bot[C-1] == E[R-1]); the lane below shuffles them in as its "north" inputs
+};
+template <int R, int C> __host__ __device__ constexpr int state_words() { return R + C; }   // E[R], up_prev, bot[0..C-2]
+
+// Geometry of the skewed wavefront: at step t (1-based) lane g works on columns col_of(t,g,0..C-1).
+template <int C> __device__ __forceinline__ int col_of(int t, int g, int c) { return C * (t - g - 1) + 1 + c; }
+template <int C> __device__ __forceinline__ int step_of(int j, int g) { return g + (j + C - 1) / C; }
+
+// Symbol selection: returns pack(s+G) for row k against column c of the current step.
+template <int R, int C>
 struct CompareSelect {
-  uint32_t q[R];      // pack(xA[row], xB[row]) raw bytes or sentinels
-  uint32_t r2;        // pack(y[j], y[j]) for the current column
+  uint32_t q[R];        // pack(symA[row], symB[row])
+  uint32_t r2[C];       // pack(y[j_c], y[j_c])
   uint32_t sel_and, sel_xor;
-  __device__ __forceinline__ void set_column(uint32_t ycode) { r2 = ycode * 0x00010001u; }
-  __device__ __forceinline__ uint32_t operator()(int k) const { return (hset2_eq(q[k], r2) & sel_and) ^ sel_xor; }
+  __device__ __forceinline__ void set_column(int c, uint32_t ysym) { r2[c] = ysym * 0x00010001u; }
+  __device__ __forceinline__ uint32_t operator()(int k, int c) const { return (hset2_eq(q[k], r2[c]) & sel_and) ^ sel_xor; }
 };
 
 // Profile selection: per-warp query profile in shared memory, word index ((code*R + k)*32 + lane).
-template <int R>
+template <int R, int C>
 struct ProfileSelect {
   const uint32_t* prof;   // shared memory, already offset by lane
-  const uint32_t* col;
-  __device__ __forceinline__ void set_column(uint32_t ycode) { col = prof + ycode * (R * 32); }
-  __device__ __forceinline__ uint32_t operator()(int k) const { return col[k * 32]; }
+  const uint32_t* col[C];
+  __device__ __forceinline__ void set_column(int c, uint32_t ycode) { col[c] = prof + ycode * (R * 32); }
+  __device__ __forceinline__ uint32_t operator()(int k, int c) const { return col[c][k * 32]; }
 };
 
-// One wavefront step for one lane: column j of rows [g*R, (g+1)*R).  Hook sees every new cell.
-//   hook(k, E_new, diag, E_old, up_in) with all values in E-space (H - G), packed s16x2.
-template <int R, bool SAT, class Select, class Hook>
-__device__ __forceinline__ void step(LaneState<R>& st, const Select& sel, const Scoring& sc, uint32_t up_cur,
+// One wavefront step for one lane: C columns of rows [g*R, (g+1)*R).  The C column chains are independent
+// up to a one-row skew, which is where the instruction-level parallelism comes from.
+//   hook(k, c, E_new): every new cell, E-space (H - G), packed s16x2.
+template <int R, int C, bool SAT, class Select, class Hook>
+__device__ __forceinline__ void step(LaneState<R, C>& st, const Select& sel, const Scoring& sc, const uint32_t (&upv)[C],
                                      uint32_t& bmax, Hook&& hook) {
-  uint32_t diag = st.up_prev;
-  uint32_t up = up_cur;
+  uint32_t above[C + 1];          // row k-1: [0] = last column of the previous step, [c+1] = column c of this step
+  above[0] = st.up_prev;
+#pragma unroll
+  for (int c = 0; c < C; ++c) above[c + 1] = upv[c];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const uint32_t sG = sel(k);
-    const uint32_t e_old = st.E[k];
-    uint32_t d = __viaddmax_s16x2_relu(diag, sG, e_old);
-    uint32_t dG = SAT ? viaddmin_s16x2(d, sc.negG2, sc.ceil2) : __vadd2(d, sc.negG2);
-    const uint32_t e_new = __viaddmax_s16x2(up, sc.negG2, dG);
-    hook(k, e_new, diag, e_old, up);
-    diag = e_old;
-    up = e_new;
-    st.E[k] = e_new;
-    bmax = __vmaxs2(bmax, e_new);
+    uint32_t cur[C + 1];
+    cur[0] = st.E[k];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t sG = sel(k, c);
+      const uint32_t d = __viaddmax_s16x2_relu(above[c], sG, cur[c]);                  // max(NW + s, W - G, 0)
+      const uint32_t dG = SAT ? viaddmin_s16x2(d, sc.negG2, sc.ceil2) : __vadd2(d, sc.negG2);   // min(., 255) - G
+      cur[c + 1] = __viaddmax_s16x2(above[c + 1], sc.negG2, dG);                       // max(N - G, .) = H - G
+      hook(k, c, cur[c + 1]);
+    }
+    if (C == 2) bmax = __vimax3_s16x2(bmax, cur[1], cur[2]);
+    else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) bmax = __vmaxs2(bmax, cur[c + 1]);
+    }
+    st.E[k] = cur[C];
+#pragma unroll
+    for (int c = 0; c <= C; ++c) above[c] = cur[c];
   }
-  st.up_prev = up_cur;
+#pragma unroll
+  for (int c = 0; c < C; ++c) st.bot[c] = above[c + 1];
+  st.up_prev = upv[C - 1];
 }
 
 struct NoHook {
-  __device__ __forceinline__ void operator()(int, uint32_t, uint32_t, uint32_t, uint32_t) const {}
+  __device__ __forceinline__ void operator()(int, int, uint32_t) const {}
 };
 
 // y symbol for column j (1-based) of a pair's range, or the sentinel outside [1, n].
@@ -146,29 +172,36 @@ __device__ __forceinline__ uint32_t load_y(const PassParams& p, const PairDesc& 
   return in ? (SYM_BASE | c) : SENT_Y;
 }
 
-template <int R>
-__device__ __forceinline__ void init_state(LaneState<R>& st, const Scoring& sc) {
+template <int R, int C>
+__device__ __forceinline__ void init_state(LaneState<R, C>& st, const Scoring& sc) {
 #pragma unroll
   for (int k = 0; k < R; ++k) st.E[k] = sc.negG2;
   st.up_prev = sc.negG2;
+#pragma unroll
+  for (int c = 0; c < C; ++c) st.bot[c] = sc.negG2;
 }
 
-// Checkpoint layout: word ((blk*(R+1) + k) * L + g), k == R holds up_prev.
-template <int R>
-__device__ __forceinline__ void save_state(const LaneState<R>& st, uint32_t* ck, int L, int g) {
+// Checkpoint layout: word ((blk*(R+C) + k) * L + g); k == R holds up_prev, k > R the extra bot[] words.
+template <int R, int C>
+__device__ __forceinline__ void save_state(const LaneState<R, C>& st, uint32_t* ck, int L, int g) {
 #pragma unroll
   for (int k = 0; k < R; ++k) ck[k * L + g] = st.E[k];
   ck[R * L + g] = st.up_prev;
+#pragma unroll
+  for (int c = 0; c < C - 1; ++c) ck[(R + 1 + c) * L + g] = st.bot[c];
 }
-template <int R>
-__device__ __forceinline__ void load_state(LaneState<R>& st, const uint32_t* ck, int L, int g) {
+template <int R, int C>
+__device__ __forceinline__ void load_state(LaneState<R, C>& st, const uint32_t* ck, int L, int g) {
 #pragma unroll
   for (int k = 0; k < R; ++k) st.E[k] = ck[k * L + g];
   st.up_prev = ck[R * L + g];
+#pragma unroll
+  for (int c = 0; c < C - 1; ++c) st.bot[c] = ck[(R + 1 + c) * L + g];
+  st.bot[C - 1] = st.E[R - 1];
 }
 
-template <int R>
-__device__ __forceinline__ void load_compare_rows(CompareSelect<R>& sel, const PassParams& p, const PairDesc& pd, int g) {
+template <int R, int C>
+__device__ __forceinline__ void load_compare_rows(CompareSelect<R, C>& sel, const PassParams& p, const PairDesc& pd, int g) {
   const uint32_t* q = p.qpairs + pd.q_off + (uint32_t)g * R;
 #pragma unroll
   for (int k = 0; k < R; ++k) sel.q[k] = __ldg(q + k);
@@ -192,10 +225,74 @@ __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassPar
   }
 }
 
+// Shared driver of both passes: restore (or initialise) the lane state, then run `nsteps` steps after
+// step t0.  All 32 lanes execute it together (full-mask shuffles); hook(k, j, E_new) fires for steps <= t1.
+template <int R, int C, bool SAT, bool PROFILE>
+struct Wavefront {
+  const PassParams& p;
+  CompareSelect<R, C> csel;
+  ProfileSelect<R, C> psel;
+  LaneState<R, C> st;
+  int L, g;
+  __device__ __forceinline__ Wavefront(const PassParams& p_) : p(p_) {}
+
+  __device__ __forceinline__ void prepare(const PairDesc& pd, uint32_t* prof_warp, int lane) {
+    if (PROFILE) {
+      build_profile<R>(prof_warp, p, pd, g, lane);     // every lane fills (and later reads) only its own column
+      psel.prof = prof_warp + lane;
+    } else {
+      load_compare_rows<R, C>(csel, p, pd, g);
+    }
+  }
+  __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
+    if (t0 == 0) init_state<R, C>(st, p.sc);
+    else load_state<R, C>(st, p.ckpt + pd.ck_off + (size_t)((t0 >> p.logB) - 1) * state_words<R, C>() * L, L, g);
+  }
+  __device__ __forceinline__ void load_symbols(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
+#pragma unroll
+    for (int c = 0; c < C; ++c) y[c] = load_y<PROFILE>(p, pd, col_of<C>(t, g, c));
+  }
+  template <class Hook>
+  __device__ __forceinline__ void one_step(int t, const uint32_t (&ycur)[C], uint32_t& bmax, Hook&& hook) {
+    uint32_t upv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      upv[c] = __shfl_up_sync(0xffffffffu, st.bot[c], 1, L);
+      if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
+    }
+    auto h = [&](int k, int c, uint32_t e_new) { hook(k, col_of<C>(t, g, c), e_new); };
+    if (PROFILE) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) psel.set_column(c, ycur[c]);
+      step<R, C, SAT>(st, psel, p.sc, upv, bmax, h);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) csel.set_column(c, ycur[c]);
+      step<R, C, SAT>(st, csel, p.sc, upv, bmax, h);
+    }
+  }
+  template <class Hook>
+  __device__ __forceinline__ void replay(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
+    restore(pd, t0);
+    uint32_t bmax = NEG_INF2;
+    uint32_t ynext[C];
+    load_symbols(pd, t0 + 1, ynext);
+    for (int s = 1; s <= nsteps; ++s) {
+      const int t = t0 + s;
+      uint32_t ycur[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
+      load_symbols(pd, t + 1, ynext);
+      const bool on = t <= t1;
+      one_step(t, ycur, bmax, [&](int k, int j, uint32_t e_new) { if (on) hook(k, j, e_new); });
+    }
+  }
+};
+
 // ======================================================================================================
 // Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp.
 // ======================================================================================================
-template <int R, bool SAT, bool PROFILE>
+template <int R, int C, bool SAT, bool PROFILE>
 __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
   const int lane = threadIdx.x & 31;
@@ -209,40 +306,31 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
   const PairDesc pd = p.pairs[pair];
 
-  LaneState<R> st;
-  init_state<R>(st, p.sc);
-  CompareSelect<R> csel;
-  ProfileSelect<R> psel;
-  if (PROFILE) {
-    uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
-    build_profile<R>(prof_warp, p, pd, g, lane);
-    psel.prof = prof_warp + lane;
-    __syncwarp();
-  } else {
-    load_compare_rows<R>(csel, p, pd, g);
-  }
+  Wavefront<R, C, SAT, PROFILE> wf(p);
+  wf.L = L; wf.g = g;
+  wf.prepare(pd, smem_prof + (size_t)warp_in_cta * p.KP * R * 32, lane);
+  wf.restore(pd, 0);
 
-  // steps t = 1 .. n + L - 1 (lane g handles column t - g); run whole blocks so every lane flushes together
+  // run whole blocks so that every lane flushes together; lanes past their range see sentinel columns
   int steps = (int)pd.nblk << p.logB;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+  steps = warp_max_i32(steps);
 
   uint32_t* blk = p.blkmax + pd.blk_off;
   uint32_t* ck = p.ckpt + pd.ck_off;
   uint32_t bmax = NEG_INF2;
-  uint32_t ynext = load_y<PROFILE>(p, pd, 1 - g);
+  uint32_t ynext[C];
+  wf.load_symbols(pd, 1, ynext);
   for (int t = 1; t <= steps; ++t) {
-    const uint32_t ycur = ynext;
-    ynext = load_y<PROFILE>(p, pd, t + 1 - g);
-    uint32_t up_cur = __shfl_up_sync(0xffffffffu, st.E[R - 1], 1, L);
-    if (g == 0) up_cur = p.sc.negG2;
-    if (PROFILE) { psel.set_column(ycur); step<R, SAT>(st, psel, p.sc, up_cur, bmax, NoHook()); }
-    else { csel.set_column(ycur); step<R, SAT>(st, csel, p.sc, up_cur, bmax, NoHook()); }
+    uint32_t ycur[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
+    wf.load_symbols(pd, t + 1, ynext);
+    wf.one_step(t, ycur, bmax, [](int, int, uint32_t) {});
     if ((t & (p.B - 1)) == 0) {
       const int b = (t >> p.logB) - 1;
       if (live && b < (int)pd.nblk) {
         blk[(size_t)b * L + g] = bmax;
-        save_state<R>(st, ck + (size_t)b * (R + 1) * L, L, g);
+        save_state<R, C>(wf.st, ck + (size_t)b * state_words<R, C>() * L, L, g);
       }
       bmax = NEG_INF2;
     }
@@ -250,7 +338,9 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
 }
 
 // ======================================================================================================
-// Pass 2: locate the reference's arg-max cell and trace back.  One group of L lanes per task.
+// Pass 2: locate the reference's arg-max cell and trace back.  One group of L lanes per task; the 32/L
+// groups of a warp run in LOCKSTEP (same instruction stream, per-group predicates), so a round costs the
+// longest group's work, not the sum.
 // ======================================================================================================
 struct TaskDesc {
   uint32_t pair;      // index into pairs
@@ -306,48 +396,8 @@ __device__ __forceinline__ int group_max_i32(int v, int L) {
   for (int o = L >> 1; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ int warp_max_i32(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 
-// Pass 2 runs the 32/L groups of a warp in LOCKSTEP: every group owns one task, all groups execute the
-// same instruction stream (restore a checkpoint, run some wavefront steps, feed a per-cell hook) and only
-// the hook is predicated per group.  The cost of a round is the longest group's, not the sum.
-template <int R, bool SAT, bool PROFILE>
-struct Replay {
-  const PassParams& p;
-  CompareSelect<R> csel;
-  ProfileSelect<R> psel;
-  LaneState<R> st;
-  int L, g;
-  __device__ __forceinline__ Replay(const PassParams& p_) : p(p_) {}
-
-  // Run `nsteps` steps (warp-uniform) starting after step t0 (per group, a multiple of B); hook(k, j, e_new)
-  // is called for steps t <= t1 (per group) only.
-  template <class Hook>
-  __device__ __forceinline__ void run(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
-    if (t0 == 0) init_state<R>(st, p.sc);
-    else load_state<R>(st, p.ckpt + pd.ck_off + (size_t)((t0 >> p.logB) - 1) * (R + 1) * L, L, g);
-    uint32_t bmax = NEG_INF2;
-    uint32_t ynext = load_y<PROFILE>(p, pd, t0 + 1 - g);
-    for (int s = 1; s <= nsteps; ++s) {
-      const int t = t0 + s;
-      const uint32_t ycur = ynext;
-      ynext = load_y<PROFILE>(p, pd, t + 1 - g);
-      uint32_t up_cur = __shfl_up_sync(0xffffffffu, st.E[R - 1], 1, L);
-      if (g == 0) up_cur = p.sc.negG2;
-      const int j = t - g;
-      const bool on = t <= t1;
-      auto h = [&](int k, uint32_t e_new, uint32_t, uint32_t, uint32_t) { if (on) hook(k, j, e_new); };
-      if (PROFILE) { psel.set_column(ycur); step<R, SAT>(st, psel, p.sc, up_cur, bmax, h); }
-      else { csel.set_column(ycur); step<R, SAT>(st, csel, p.sc, up_cur, bmax, h); }
-    }
-  }
-};
-
-template <int R, bool SAT, bool PROFILE>
+template <int R, int C, bool SAT, bool PROFILE>
 __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
   extern __shared__ uint32_t smem_prof[];
   const PassParams& p = tp.pp;
@@ -366,9 +416,10 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
   const int row0 = g * R + 1;          // first H row of this lane
   const uint32_t gshift = (uint32_t)(grp_in_warp * L);
   const uint32_t gbits = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+  const int CB = C << p.logB;          // columns per block of steps
 
-  Replay<R, SAT, PROFILE> rp(p);
-  rp.L = L; rp.g = g;
+  Wavefront<R, C, SAT, PROFILE> wf(p);
+  wf.L = L; wf.g = g;
 
   for (int base = gwarp * groups_per_warp; base < tp.ntasks; base += nwarps * groups_per_warp) {   // warp-uniform
     const int ti = base + grp_in_warp;
@@ -380,14 +431,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     const uint32_t half = td.half;
     const uint8_t* xraw = p.reads_raw + (td.half ? pd.xB : pd.xA);
     const uint8_t* yraw = p.ref_raw + pd.y_off;
-
-    if (PROFILE) {
-      uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
-      build_profile<R>(prof_warp, p, pd, g, lane);     // every lane fills (and later reads) only its own column
-      rp.psel.prof = prof_warp + lane;
-    } else {
-      load_compare_rows<R>(rp.csel, p, pd, g);
-    }
+    wf.prepare(pd, smem_prof + (size_t)warp_in_cta * p.KP * R * 32, lane);
 
     // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------------
     const uint32_t* blk = p.blkmax + pd.blk_off;
@@ -412,8 +456,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     uint64_t best = ~0ull;
     int b_wrap = (int)pd.nblk;           // blocks >= b_wrap may hold wrapped (lower-triangle) cells: visited first
     if (tp.mode == MODE_SAT_U8) {
-      const int need = ncols_raw - m;
-      b_wrap = max(0, ((need + p.B - 1) >> p.logB) - 1);
+      const int need = ncols_raw - m;    // a block may wrap iff its last column >= need
+      b_wrap = max(0, (need + CB - 1) / CB - 1);
       if (b_wrap > (int)pd.nblk) b_wrap = (int)pd.nblk;
     }
     int cursor = active ? 0 : 2 * (int)pd.nblk;     // positions 0..nblk-b_wrap-1 -> wrapped part, then the rest
@@ -421,7 +465,6 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     const uint32_t vmax2 = (uint32_t)(uint16_t)(int16_t)vmax * 0x00010001u;
     const uint32_t hmask = half ? 0xFFFF0000u : 0x0000FFFFu;
     while (true) {
-      // each group advances its cursor to its next admissible candidate block (L blocks per probe)
       int myb = -1;
       while (true) {                                   // warp-uniform loop; the body is predicated per group
         const bool searching = cursor < (int)pd.nblk && myb < 0;
@@ -435,7 +478,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
           for (int q = 0; q < L; ++q) bm = max(bm, half_of(blk[(size_t)b * L + q], half));
           if (bm == vmax) {
             const int t0 = b << p.logB;
-            const int jmin = max(1, t0 + 1 - (L - 1)), jmax = min(n, t0 + p.B);
+            const int jmin = max(1, C * (t0 - (L - 1)) + 1), jmax = min(n, C * (t0 + p.B));
             if (jmin <= jmax) {
               uint64_t lb;
               if (tp.mode == MODE_SAT_U8) lb = (jmax + m >= ncols_raw) ? 0ull : ((uint64_t)(uint32_t)(jmin + 1) << 32);
@@ -455,7 +498,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
       const bool has = myb >= 0;
       const int t0 = has ? (myb << p.logB) : 0;
       uint64_t mine = ~0ull;
-      rp.run(pd, t0, has ? t0 + p.B : -1, p.B, [&](int k, int j, uint32_t e_new) {
+      wf.replay(pd, t0, has ? t0 + p.B : -1, p.B, [&](int k, int j, uint32_t e_new) {
         if (((e_new ^ vmax2) & hmask) == 0) {
           const int i = row0 + k;
           if (i <= m && j >= 1 && j <= n) {
@@ -496,22 +539,22 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     bool done = !active;
     while (!__all_sync(0xffffffffu, done)) {
       const int l_e = (ix - 1) / R;
-      const int t_hi = done ? 0 : iy + l_e;
+      const int t_hi = done ? 0 : step_of<C>(iy, l_e);
       int c_lo = iy - 2 - (ix + 8);      // restart at a checkpoint left of the columns the remaining rows can reach
       if (c_lo < 0) c_lo = 0;
-      const int t_lo = done ? 0 : ((c_lo >> p.logB) << p.logB);
-      const int valid_lo = max(t_lo, t_hi - tp.Wc + 1);     // oldest column every lane still holds
+      const int t_lo = done ? 0 : (((c_lo / C) >> p.logB) << p.logB);
+      const int valid_lo = max(C * t_lo, C * t_hi - tp.Wc + 1);     // oldest column every lane still holds
       if (!done && t_lo > 0) {
-        // the checkpoint itself is column t_lo - g of this lane's rows
-        const uint32_t* ck = p.ckpt + pd.ck_off + (size_t)((t_lo >> p.logB) - 1) * (R + 1) * L;
-        const int jc = t_lo - g;
+        // the checkpoint itself is column C * (t_lo - g) of this lane's rows
+        const uint32_t* ck = p.ckpt + pd.ck_off + (size_t)((t_lo >> p.logB) - 1) * state_words<R, C>() * L;
+        const int jc = C * (t_lo - g);
         if (jc >= 0) {
 #pragma unroll
           for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + row0 + k] = ck[k * L + g];
         }
       }
       const int nsteps = warp_max_i32(t_hi - t_lo);
-      rp.run(pd, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
+      wf.replay(pd, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
         if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + row0 + k] = e_new;
       });
       __syncwarp();
@@ -548,6 +591,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
   }
 }
 
+#ifdef SWB_HELPER_KERNELS
 // ======================================================================================================
 // Small helper kernels
 // ======================================================================================================
@@ -588,5 +632,7 @@ __global__ void select_piece_kernel(const int32_t* task_max, int nreads, int npi
   }
   winner_task[r] = (uint32_t)(r * npiece + bp);
 }
+
+#endif  // SWB_HELPER_KERNELS
 
 }  // namespace swb

@@ -1,0 +1,40 @@
+// sw_inst.cu — explicit instantiation of the wavefront kernels for ONE rows-per-lane value (-DSWB_R=<R>).
+// build.py compiles this file once per R in parallel and links the objects into libswb200.so.
+#include "sw_core.cuh"
+
+#ifndef SWB_R
+#error "compile with -DSWB_R=<rows per lane>"
+#endif
+#define SWB_CAT2(a, b) a##b
+#define SWB_CAT(a, b) SWB_CAT2(a, b)
+
+using namespace swb;
+
+namespace {
+template <class K, class P>
+cudaError_t go(K k, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& p) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<grid, block, smem, st>>>(p);
+  return cudaGetLastError();
+}
+template <int C>
+cudaError_t score_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  if (profile) return sat ? go(score_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(score_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
+  return sat ? go(score_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(score_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
+}
+template <int C>
+cudaError_t trace_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+  if (profile) return sat ? go(trace_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
+  return sat ? go(trace_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(trace_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
+}
+}  // namespace
+
+cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  return C == 1 ? score_c<1>(sat, profile, grid, block, smem, st, p) : score_c<2>(sat, profile, grid, block, smem, st, p);
+}
+cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+  return C == 1 ? trace_c<1>(sat, profile, grid, block, smem, st, p) : trace_c<2>(sat, profile, grid, block, smem, st, p);
+}

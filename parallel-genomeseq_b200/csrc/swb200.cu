@@ -20,9 +20,17 @@
 #include <string>
 #include <vector>
 
+#define SWB_HELPER_KERNELS 1
 #include "sw_core.cuh"
 
 using namespace swb;
+
+// one translation unit per rows-per-lane value R (csrc/sw_inst.cu compiled with -DSWB_R=<R>)
+#define SWB_DECL(RR)                                                                                                  \
+  cudaError_t swb_launch_score_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p); \
+  cudaError_t swb_launch_trace_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p);
+SWB_DECL(2) SWB_DECL(4) SWB_DECL(5) SWB_DECL(8) SWB_DECL(12) SWB_DECL(16) SWB_DECL(19) SWB_DECL(24) SWB_DECL(32)
+#undef SWB_DECL
 
 namespace {
 
@@ -89,6 +97,7 @@ struct swb_ctx {
   unsigned flags = 0;
   size_t cons_stride = 0;
   int B = 64, logB = 6;
+  int C = 1;                        // columns per wavefront step (2 = more ILP per warp; measured slower on B200, kept selectable)
   std::vector<uint64_t> offsets;
   std::vector<char> seq_host;       // kept for the custom-scoring re-alignment of the chunked path
   std::vector<LaunchClass> classes;
@@ -148,7 +157,9 @@ bool use_profile(const swb_ctx* ctx, bool force_default) {
   if (!hs.match_shaped && !force_default) return true;
   if (force_default && !hs.is_default()) return false;      // the profile table holds the constructor's scoring
   if (const char* e = getenv("SWB_SELECT")) { if (!strcmp(e, "profile")) return ctx->KP <= 64; if (!strcmp(e, "compare")) return false; }
-  return false;
+  // match/mismatch scoring: the profile costs no ALU instruction per cell (one LDS instead of HSET2 + LOP3)
+  // and wins whenever the alphabet is small enough to keep 16 warps per SM resident (measured: +22 % on DNA)
+  return ctx->KP <= 6;
 }
 
 Scoring device_scoring(const HostScoring& hs, bool force_default) {
@@ -164,50 +175,23 @@ Scoring device_scoring(const HostScoring& hs, bool force_default) {
   return s;
 }
 
-// ---- kernel dispatch over the compiled (R, SAT, PROFILE) instantiations --------------------------------
-template <int R>
-cudaError_t launch_score_r(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
-  if (profile) {
-    auto k = sat ? score_kernel<R, true, true> : score_kernel<R, false, true>;
-    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-    k<<<grid, block, smem, st>>>(p);
-  } else {
-    auto k = sat ? score_kernel<R, true, false> : score_kernel<R, false, false>;
-    k<<<grid, block, 0, st>>>(p);
-  }
-  return cudaGetLastError();
-}
-template <int R>
-cudaError_t launch_trace_r(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
-  if (profile) {
-    auto k = sat ? trace_kernel<R, true, true> : trace_kernel<R, false, true>;
-    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-    k<<<grid, block, smem, st>>>(p);
-  } else {
-    auto k = sat ? trace_kernel<R, true, false> : trace_kernel<R, false, false>;
-    k<<<grid, block, 0, st>>>(p);
-  }
-  return cudaGetLastError();
-}
-cudaError_t launch_score(int R, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
-#define CALL_SCORE(RR) launch_score_r<RR>(sat, profile, grid, block, smem, st, p)
+// ---- kernel dispatch: one translation unit per R (sw_inst.cu compiled with -DSWB_R=<R>) ------------------
+
+cudaError_t launch_score(int R, int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
   switch (R) {
-    case 2: return CALL_SCORE(2); case 4: return CALL_SCORE(4); case 5: return CALL_SCORE(5);
-    case 8: return CALL_SCORE(8); case 12: return CALL_SCORE(12); case 16: return CALL_SCORE(16);
-    case 19: return CALL_SCORE(19); case 24: return CALL_SCORE(24); case 32: return CALL_SCORE(32);
+#define SWB_CASE(RR) case RR: return swb_launch_score_r##RR(C, sat, profile, grid, block, smem, st, p);
+    SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
+#undef SWB_CASE
     default: return cudaErrorInvalidValue;
   }
-#undef CALL_SCORE
 }
-cudaError_t launch_trace(int R, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
-#define CALL_TRACE(RR) launch_trace_r<RR>(sat, profile, grid, block, smem, st, p)
+cudaError_t launch_trace(int R, int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
   switch (R) {
-    case 2: return CALL_TRACE(2); case 4: return CALL_TRACE(4); case 5: return CALL_TRACE(5);
-    case 8: return CALL_TRACE(8); case 12: return CALL_TRACE(12); case 16: return CALL_TRACE(16);
-    case 19: return CALL_TRACE(19); case 24: return CALL_TRACE(24); case 32: return CALL_TRACE(32);
+#define SWB_CASE(RR) case RR: return swb_launch_trace_r##RR(C, sat, profile, grid, block, smem, st, p);
+    SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
+#undef SWB_CASE
     default: return cudaErrorInvalidValue;
   }
-#undef CALL_TRACE
 }
 
 // Upload the (s + G) table of the profile select: [257][KP] int16, row 256 / column KP-1 = sentinels.
@@ -242,16 +226,22 @@ struct TaskSeed { uint32_t read; uint32_t piece; uint32_t y_off; uint32_t n; uin
 int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, std::vector<LaunchClass>* out) {
   out->clear();
   const bool profile = use_profile(ctx, false);
-  int r_cap = 32;
-  if (profile) r_cap = std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128))));
+  // rows per lane: up to 32 registers; with the profile select prefer a per-warp profile <= 14 KB (16 warps / SM)
+  // and never exceed what one warp's profile can hold in shared memory
+  const int r_hard = profile ? std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128)))) : 32;
+  const int r_pref = profile ? std::max(2, std::min(r_hard, (int)(14336 / ((size_t)ctx->KP * 128)))) : 32;
   // geometry per distinct m
   std::map<uint32_t, size_t> count_by_m;
   for (auto& s : seeds) count_by_m[s.m]++;
   std::map<uint32_t, Geometry> geo_by_m;
   for (auto& kv : count_by_m) {
     Geometry g;
+    int r_cap = r_pref;
+    const int need = ((int)kv.first + 31) / 32;
+    for (int i = 0; i < kNumR && r_cap < need; ++i) if (kRSet[i] >= need) r_cap = kRSet[i];
+    r_cap = std::min(r_cap, r_hard);
     if (!choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g))
-      return fail(ctx, SWB_ERR_UNSUPPORTED, "sequence of " + std::to_string(kv.first) + " rows exceeds 32 lanes x " + std::to_string(r_cap) + " rows (long-read striping is not built yet)");
+      return fail(ctx, SWB_ERR_UNSUPPORTED, "sequence of " + std::to_string(kv.first) + " rows exceeds 32 lanes x " + std::to_string(r_hard) + " rows (long-sequence row striping is not built yet)");
     geo_by_m[kv.first] = g;
   }
   std::map<std::pair<int, int>, int> class_of;   // (L, R) -> class index
@@ -288,7 +278,7 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       const TaskSeed& a = seeds[id[order[k]]];
       PairDesc pd{};
       pd.y_off = a.y_off; pd.n = a.n;
-      pd.nblk = (uint32_t)((a.n + L - 1 + ctx->B - 1) / ctx->B);
+      pd.nblk = (uint32_t)(((a.n + ctx->C - 1) / ctx->C + L - 1 + ctx->B - 1) / ctx->B);
       pd.mA = a.m; pd.xA = a.x_off;
       const uint32_t pair_idx = (uint32_t)lc.pairs.size();
       lc.tasks[order[k]] = TaskDesc{pair_idx, 0u, a.read, a.y_off};
@@ -305,7 +295,7 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       ++k;
       pd.q_off = (uint32_t)lc.q_words; lc.q_words += (size_t)L * R;
       pd.blk_off = lc.blk_words; lc.blk_words += (size_t)pd.nblk * L;
-      pd.ck_off = lc.ck_words; lc.ck_words += (size_t)pd.nblk * (R + 1) * L;
+      pd.ck_off = lc.ck_words; lc.ck_words += (size_t)pd.nblk * (R + ctx->C) * L;
       lc.pairs.push_back(pd);
     }
     if (lc.q_words > 0xFFFFFFFFull) return fail(ctx, SWB_ERR_UNSUPPORTED, "batch too large for one launch class (split the batch)");
@@ -374,9 +364,9 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     {
       const size_t warps = (lc.pairs.size() + groups_per_warp - 1) / groups_per_warp;
       const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
-      CUDA_TRY(launch_score(R, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
+      CUDA_TRY(launch_score(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
       ctx->stats.kernel_launches++;
-      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nblk * ctx->B * L * R * 2ull;
+      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nblk * ctx->B * ctx->C * L * R * 2ull;
     }
     if (!trace && !select_pieces) continue;
 
@@ -403,7 +393,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.task_list = task_list;
     tp.ntasks = ntrace;
     tp.mode = hs.mode;
-    int wc = 64; while (wc < L * R + L + 24) wc <<= 1;
+    int wc = 64; while (wc < L * R + ctx->C * L + 24) wc <<= 1;
     tp.Wc = wc; tp.rstride = L * R + 1;
     const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(uint32_t);
     size_t max_groups = (size_t)148 * 16 * groups_per_warp;
@@ -425,10 +415,10 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.want_consensus = (ctx->flags & SWB_FLAG_CONSENSUS) ? 1 : 0;
     if (!tp.want_consensus) tp.cons_cap = 0x7FFFFFFFu;
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CUDA_TRY(launch_trace(R, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
+    CUDA_TRY(launch_trace(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
     CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->stats.kernel_launches++;
-    ctx->stats.cells_pass2 += (uint64_t)ntrace * (uint64_t)(3 * ctx->B + lc.max_m + 16) * L * R * 2ull;
+    ctx->stats.cells_pass2 += (uint64_t)ntrace * (uint64_t)(3 * ctx->B * ctx->C + lc.max_m + 16) * L * R * 2ull;
     ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
   }
   return SWB_OK;
@@ -623,7 +613,9 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     if (const char* e = getenv("SWB_CKPT_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
     const double words_per_block = (double)((seeds.size() + 1) / 2) * ((double)max_m * 1.08 + 40.0);
     int B = 32;
-    while (B < 65536 && words_per_block * 4.0 * ((double)max_n / B + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
+    ctx->C = 1;
+    if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
+    while (B < 65536 && words_per_block * 4.0 * ((double)max_n / ((double)B * ctx->C) + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
     ctx->B = B; ctx->logB = ilog2(B);
   }
   int rc = upload_profile_table(ctx);

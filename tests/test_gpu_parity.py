@@ -146,3 +146,32 @@ def test_chunk_range_error(engine, pkg):
     with pytest.raises(pkg.SwbError) as ei:
         engine.align(["ACGTACGTAC" * 10], npiece=4, ratio=2.0)
     assert ei.value.code == -3
+
+
+def test_cpp_shims_and_driver(tmp_path, data_small):
+    """The C++ drop-in layer: the reference's unit tests with the aligner type swapped (tests/cpp/test_shim.cpp)
+    and the batched sw_solve_small driver, whose output CSV must carry the reference's pos/score columns."""
+    import os
+    import subprocess
+    from conftest import ROOT, GOLDEN
+    exe = os.path.join(ROOT, "tests", "cpp", "test_shim")
+    if not os.path.isfile(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
+                               "-L", os.path.join(ROOT, "parallel-genomeseq_b200"), "-lswb200", "-Wl,-rpath," + os.path.join(ROOT, "parallel-genomeseq_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SHIM OK" in out.stdout, out.stdout + out.stderr
+    drv = os.path.join(ROOT, "parallel-genomeseq_b200", "drivers", "sw_solve_small")
+    if not os.path.isfile(drv):
+        subprocess.check_call(["make", "-C", os.path.dirname(drv)])
+    for args, gold in (([], "data_small_sw_skewed.csv"), (["--npiece", "17", "--ratio", "2.0"], "data_small_p17.csv"), (["--float"], "data_small_sw_float.csv")):
+        csv_out = str(tmp_path / "align_output.csv")
+        r = subprocess.run([drv, os.path.join(GOLDEN, "data_small", "genome.chr22.5K.fa"), os.path.join(GOLDEN, "data_small", "data_small_ground_truth.csv"), csv_out] + args,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "GCUP:" in r.stdout, r.stdout + r.stderr
+        want = read_golden_csv(gold)
+        with open(csv_out) as f:
+            rows = f.read().strip().split("\n")
+        assert rows[0].endswith(",pos_pred,score") and len(rows) == 1171
+        for line, g in zip(rows[1:], want):
+            f_ = line.split(", ")
+            assert int(f_[-2]) == g["pos"] and float(f_[-1]) == g["score"]
