@@ -40,8 +40,11 @@ struct PairDesc {
   uint32_t nblk;      // ceil((L - 1 + ceil(n / C)) / B) blocks of B steps
   uint32_t mA, mB;    // real row counts (0 = empty half)
   uint32_t xA, xB;    // byte offsets of the raw sequences in reads_raw
-  uint64_t blk_off;   // word offset into blkmax: nblk * L words
-  uint64_t ck_off;    // word offset into ckpt  : nblk * (R+C) * L words
+  uint64_t blk_off;   // word offset into blkmax: nstrips * nblk * L words
+  uint64_t ck_off;    // word offset into ckpt  : nstrips * nblk * (R+C) * L words
+  uint64_t bnd_off;   // word offset into bnd   : (nstrips-1) * (n+1) words (bottom row of every strip but the last)
+  uint32_t nstrips;   // row strips of L*R rows (1 unless the sequences are longer than one warp can hold; then L == 32)
+  uint32_t pad_;
 };
 
 struct Scoring {
@@ -63,6 +66,7 @@ struct PassParams {
   int npairs;
   uint32_t* blkmax;
   uint32_t* ckpt;
+  uint32_t* bnd;               // strip boundary rows (packed E words), see PairDesc::bnd_off
   int L, logL, B, logB;
   Scoring sc;
 };
@@ -227,38 +231,68 @@ __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassPar
 
 // Shared driver of both passes: restore (or initialise) the lane state, then run `nsteps` steps after
 // step t0.  All 32 lanes execute it together (full-mask shuffles); hook(k, j, E_new) fires for steps <= t1.
+//
+// Row strips: a pair whose sequences do not fit L*R rows is cut into nstrips strips of L*R rows (L == 32).
+// Strips run top to bottom; the last row of strip s is written to a boundary row in HBM (one packed word
+// per column) and read back as the "north" input of strip s+1 — 32 columns per coalesced load, handed to
+// lane 0 with one shuffle per step.  BND selects that code path (compiled out for single-strip launches).
 template <int R, int C, bool SAT, bool PROFILE>
 struct Wavefront {
   const PassParams& p;
   CompareSelect<R, C> csel;
   ProfileSelect<R, C> psel;
   LaneState<R, C> st;
-  int L, g;
+  int L, g, lane;
+  int strip = 0;
+  const uint32_t* bnd_in = nullptr;   // boundary row above this strip (indexed by column), null for strip 0
+  uint32_t* bnd_out = nullptr;        // boundary row below this strip, null for the last strip
+  uint32_t chunk_cur = 0, chunk_next = 0;
   __device__ __forceinline__ Wavefront(const PassParams& p_) : p(p_) {}
 
-  __device__ __forceinline__ void prepare(const PairDesc& pd, uint32_t* prof_warp, int lane) {
+  __device__ __forceinline__ size_t blk_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * L; }
+  __device__ __forceinline__ size_t ck_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * state_words<R, C>() * L; }
+
+  // select the strip and load its rows (registers or shared-memory profile)
+  __device__ __forceinline__ void prepare(const PairDesc& pd, int s, uint32_t* prof_warp) {
+    strip = s;
+    bnd_in = s > 0 ? p.bnd + pd.bnd_off + (size_t)(s - 1) * (pd.n + 1) : nullptr;
+    bnd_out = (s + 1 < (int)pd.nstrips) ? p.bnd + pd.bnd_off + (size_t)s * (pd.n + 1) : nullptr;
+    PairDesc sp = pd;
+    sp.q_off = pd.q_off + (uint32_t)s * (uint32_t)(L * R);
     if (PROFILE) {
-      build_profile<R>(prof_warp, p, pd, g, lane);     // every lane fills (and later reads) only its own column
+      build_profile<R>(prof_warp, p, sp, g, lane);     // every lane fills (and later reads) only its own column
       psel.prof = prof_warp + lane;
     } else {
-      load_compare_rows<R, C>(csel, p, pd, g);
+      load_compare_rows<R, C>(csel, p, sp, g);
     }
   }
   __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
     if (t0 == 0) init_state<R, C>(st, p.sc);
-    else load_state<R, C>(st, p.ckpt + pd.ck_off + (size_t)((t0 >> p.logB) - 1) * state_words<R, C>() * L, L, g);
+    else load_state<R, C>(st, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
   }
   __device__ __forceinline__ void load_symbols(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
 #pragma unroll
     for (int c = 0; c < C; ++c) y[c] = load_y<PROFILE>(p, pd, col_of<C>(t, g, c));
   }
-  template <class Hook>
-  __device__ __forceinline__ void one_step(int t, const uint32_t (&ycur)[C], uint32_t& bmax, Hook&& hook) {
+  // 32 boundary columns starting at column 32*k + 1, one per lane
+  __device__ __forceinline__ uint32_t load_chunk(const PairDesc& pd, int k) const {
+    const int j = 32 * k + 1 + lane;
+    return (bnd_in && j <= (int)pd.n) ? bnd_in[j] : p.sc.negG2;
+  }
+  template <bool BND, class Hook>
+  __device__ __forceinline__ void one_step(const PairDesc& pd, int t, const uint32_t (&ycur)[C], uint32_t& bmax, Hook&& hook) {
     uint32_t upv[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       upv[c] = __shfl_up_sync(0xffffffffu, st.bot[c], 1, L);
-      if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
+      if (BND) {                                          // C == 1, L == 32: lane 0 works on column t
+        const int i = (t - 1) & 31;
+        if (i == 0) { chunk_cur = chunk_next; chunk_next = load_chunk(pd, ((t - 1) >> 5) + 1); }
+        const uint32_t north = __shfl_sync(0xffffffffu, chunk_cur, i);
+        if (g == 0) upv[c] = north;
+      } else {
+        if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
+      }
     }
     auto h = [&](int k, int c, uint32_t e_new) { hook(k, col_of<C>(t, g, c), e_new); };
     if (PROFILE) {
@@ -270,10 +304,19 @@ struct Wavefront {
       for (int c = 0; c < C; ++c) csel.set_column(c, ycur[c]);
       step<R, C, SAT>(st, csel, p.sc, upv, bmax, h);
     }
+    if (BND) {
+      const int j = col_of<C>(t, g, 0);
+      if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) bnd_out[j] = st.bot[0];
+    }
   }
-  template <class Hook>
-  __device__ __forceinline__ void replay(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
+  template <bool BND>
+  __device__ __forceinline__ void begin(const PairDesc& pd, int t0) {
     restore(pd, t0);
+    if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
+  }
+  template <bool BND, class Hook>
+  __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
+    begin<BND>(pd, t0);
     uint32_t bmax = NEG_INF2;
     uint32_t ynext[C];
     load_symbols(pd, t0 + 1, ynext);
@@ -284,14 +327,47 @@ struct Wavefront {
       for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
       load_symbols(pd, t + 1, ynext);
       const bool on = t <= t1;
-      one_step(t, ycur, bmax, [&](int k, int j, uint32_t e_new) { if (on) hook(k, j, e_new); });
+      one_step<BND>(pd, t, ycur, bmax, [&](int k, int j, uint32_t e_new) { if (on) hook(k, j, e_new); });
     }
+  }
+  // replay never writes boundary rows again (bnd_out is cleared), it only reads them
+  template <class Hook>
+  __device__ __forceinline__ void replay(const PairDesc& pd, bool multi, int t0, int t1, int nsteps, Hook&& hook) {
+    bnd_out = nullptr;
+    if (C == 1 && multi) replay_impl<true>(pd, t0, t1, nsteps, hook);
+    else replay_impl<false>(pd, t0, t1, nsteps, hook);
   }
 };
 
 // ======================================================================================================
 // Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp.
 // ======================================================================================================
+template <int R, int C, bool SAT, bool PROFILE, bool BND>
+__device__ __forceinline__ void score_strip(Wavefront<R, C, SAT, PROFILE>& wf, const PassParams& p, const PairDesc& pd, int steps, bool live) {
+  const int L = wf.L, g = wf.g;
+  uint32_t* blk = p.blkmax + pd.blk_off;
+  uint32_t* ck = p.ckpt + pd.ck_off;
+  wf.template begin<BND>(pd, 0);
+  uint32_t bmax = NEG_INF2;
+  uint32_t ynext[C];
+  wf.load_symbols(pd, 1, ynext);
+  for (int t = 1; t <= steps; ++t) {
+    uint32_t ycur[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
+    wf.load_symbols(pd, t + 1, ynext);
+    wf.template one_step<BND>(pd, t, ycur, bmax, [](int, int, uint32_t) {});
+    if ((t & (p.B - 1)) == 0) {
+      const int b = (t >> p.logB) - 1;
+      if (live && b < (int)pd.nblk) {
+        blk[wf.blk_index(pd, b) + g] = bmax;
+        save_state<R, C>(wf.st, ck + wf.ck_index(pd, b), L, g);
+      }
+      bmax = NEG_INF2;
+    }
+  }
+}
+
 template <int R, int C, bool SAT, bool PROFILE>
 __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
@@ -307,33 +383,22 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   const PairDesc pd = p.pairs[pair];
 
   Wavefront<R, C, SAT, PROFILE> wf(p);
-  wf.L = L; wf.g = g;
-  wf.prepare(pd, smem_prof + (size_t)warp_in_cta * p.KP * R * 32, lane);
-  wf.restore(pd, 0);
+  wf.L = L; wf.g = g; wf.lane = lane;
+  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
 
   // run whole blocks so that every lane flushes together; lanes past their range see sentinel columns
-  int steps = (int)pd.nblk << p.logB;
-  steps = warp_max_i32(steps);
-
-  uint32_t* blk = p.blkmax + pd.blk_off;
-  uint32_t* ck = p.ckpt + pd.ck_off;
-  uint32_t bmax = NEG_INF2;
-  uint32_t ynext[C];
-  wf.load_symbols(pd, 1, ynext);
-  for (int t = 1; t <= steps; ++t) {
-    uint32_t ycur[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
-    wf.load_symbols(pd, t + 1, ynext);
-    wf.one_step(t, ycur, bmax, [](int, int, uint32_t) {});
-    if ((t & (p.B - 1)) == 0) {
-      const int b = (t >> p.logB) - 1;
-      if (live && b < (int)pd.nblk) {
-        blk[(size_t)b * L + g] = bmax;
-        save_state<R, C>(wf.st, ck + (size_t)b * state_words<R, C>() * L, L, g);
-      }
-      bmax = NEG_INF2;
+  const int steps = warp_max_i32((int)pd.nblk << p.logB);
+  const int nstrips = warp_max_i32((int)pd.nstrips);    // > 1 only with L == 32 (one pair per warp)
+  if (C == 1 && nstrips > 1) {
+    for (int s = 0; s < nstrips; ++s) {
+      wf.prepare(pd, s, prof_warp);
+      score_strip<R, C, SAT, PROFILE, true>(wf, p, pd, steps, live);
+      __syncwarp();                       // boundary row of strip s is complete before strip s+1 reads it
+      __threadfence_block();
     }
+  } else {
+    wf.prepare(pd, 0, prof_warp);
+    score_strip<R, C, SAT, PROFILE, false>(wf, p, pd, steps, live);
   }
 }
 
@@ -413,13 +478,13 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
   uint32_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;
   const int wmask = tp.Wc - 1;
   const int G = p.sc.G;
-  const int row0 = g * R + 1;          // first H row of this lane
+  const int S = L * R;                 // rows per strip
   const uint32_t gshift = (uint32_t)(grp_in_warp * L);
   const uint32_t gbits = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
-  const int CB = C << p.logB;          // columns per block of steps
+  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
 
   Wavefront<R, C, SAT, PROFILE> wf(p);
-  wf.L = L; wf.g = g;
+  wf.L = L; wf.g = g; wf.lane = lane;
 
   for (int base = gwarp * groups_per_warp; base < tp.ntasks; base += nwarps * groups_per_warp) {   // warp-uniform
     const int ti = base + grp_in_warp;
@@ -428,15 +493,19 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     const PairDesc pd = p.pairs[td.pair];
     const int m = td.half ? pd.mB : pd.mA;
     const int n = pd.n;
+    const int nblk = (int)pd.nblk;
+    const int nunits = nblk * (int)pd.nstrips;       // (strip, block) units
+    const bool multi = warp_max_i32((int)pd.nstrips) > 1;   // > 1 only with L == 32: one group per warp
     const uint32_t half = td.half;
     const uint8_t* xraw = p.reads_raw + (td.half ? pd.xB : pd.xA);
     const uint8_t* yraw = p.ref_raw + pd.y_off;
-    wf.prepare(pd, smem_prof + (size_t)warp_in_cta * p.KP * R * 32, lane);
+    int cur_strip = 0;
+    wf.prepare(pd, 0, prof_warp);
 
     // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------------
     const uint32_t* blk = p.blkmax + pd.blk_off;
     int vmax = -32768;
-    for (uint32_t w = g; w < pd.nblk * (uint32_t)L; w += L) vmax = max(vmax, half_of(blk[w], half));
+    for (uint32_t w = g; w < (uint32_t)nunits * (uint32_t)L; w += L) vmax = max(vmax, half_of(blk[w], half));
     vmax = group_max_i32(vmax, L);
     const int score = vmax + G;
     if (active && (m == 0 || score <= 0)) {
@@ -449,56 +518,57 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     }
 
     // ---- 2. arg-max with the reference's tie-break --------------------------------------------------------
-    // Candidate blocks: some lane's block maximum equals vmax.  Their cells are recomputed and keyed; the
-    // smallest key wins (skewed raw order for SAT_U8, column-major for EXACT).  Blocks whose smallest
-    // possible key already exceeds the current winner are skipped.
+    // Candidate units: some lane's block maximum equals vmax.  Their cells are recomputed and keyed; the
+    // smallest key wins (skewed raw order for SAT_U8, column-major for EXACT).  Units whose smallest possible
+    // key already exceeds the current winner are skipped; units that may hold wrapped (lower-triangle) cells
+    // sort first in the skewed order and are visited first (phase 0), the others in phase 1.
     const int ncols_raw = max(n + 1, m + 1);
     uint64_t best = ~0ull;
-    int b_wrap = (int)pd.nblk;           // blocks >= b_wrap may hold wrapped (lower-triangle) cells: visited first
-    if (tp.mode == MODE_SAT_U8) {
-      const int need = ncols_raw - m;    // a block may wrap iff its last column >= need
-      b_wrap = max(0, (need + CB - 1) / CB - 1);
-      if (b_wrap > (int)pd.nblk) b_wrap = (int)pd.nblk;
-    }
-    int cursor = active ? 0 : 2 * (int)pd.nblk;     // positions 0..nblk-b_wrap-1 -> wrapped part, then the rest
-    const int n_first = (int)pd.nblk - b_wrap;
+    int cursor = active ? 0 : 2 * nunits;            // [0, nunits): phase 0, [nunits, 2*nunits): phase 1
     const uint32_t vmax2 = (uint32_t)(uint16_t)(int16_t)vmax * 0x00010001u;
     const uint32_t hmask = half ? 0xFFFF0000u : 0x0000FFFFu;
     while (true) {
-      int myb = -1;
+      int myu = -1;
       while (true) {                                   // warp-uniform loop; the body is predicated per group
-        const bool searching = cursor < (int)pd.nblk && myb < 0;
+        const bool searching = cursor < 2 * nunits && myu < 0;
         if (!__any_sync(0xffffffffu, searching)) break;
         const int pos = cursor + g;
         bool cand = false;
-        int b = -1;
-        if (searching && pos < (int)pd.nblk) {
-          b = pos < n_first ? b_wrap + pos : pos - n_first;
+        int u = -1;
+        if (searching && pos < 2 * nunits) {
+          const int phase = pos >= nunits;
+          u = pos - phase * nunits;
+          const int us = u / nblk, ub = u - us * nblk;
           int bm = -32768;
-          for (int q = 0; q < L; ++q) bm = max(bm, half_of(blk[(size_t)b * L + q], half));
+          for (int q = 0; q < L; ++q) bm = max(bm, half_of(blk[(size_t)u * L + q], half));
           if (bm == vmax) {
-            const int t0 = b << p.logB;
+            const int t0 = ub << p.logB;
             const int jmin = max(1, C * (t0 - (L - 1)) + 1), jmax = min(n, C * (t0 + p.B));
-            if (jmin <= jmax) {
+            const int imin = us * S + 1, imax = min(m, (us + 1) * S);
+            if (jmin <= jmax && imin <= imax) {
+              const bool wraps = tp.mode == MODE_SAT_U8 && (jmax + imax >= ncols_raw);
               uint64_t lb;
-              if (tp.mode == MODE_SAT_U8) lb = (jmax + m >= ncols_raw) ? 0ull : ((uint64_t)(uint32_t)(jmin + 1) << 32);
+              if (tp.mode == MODE_SAT_U8) lb = wraps ? 0ull : ((uint64_t)(uint32_t)(jmin + imin) << 32);
               else lb = (uint64_t)(uint32_t)jmin << 32;
-              cand = lb <= best;
+              cand = (lb <= best) && (wraps == (phase == 0));
             }
           }
         }
         const uint32_t cm = (__ballot_sync(0xffffffffu, cand) >> gshift) & gbits;
         const int q = cm ? __ffs(cm) - 1 : 0;
-        const int bsel = __shfl_sync(0xffffffffu, b, (int)gshift + q);
+        const int usel = __shfl_sync(0xffffffffu, u, (int)gshift + q);
         if (searching) {
-          if (cm) { myb = bsel; cursor += q + 1; } else { cursor += L; }
+          if (cm) { myu = usel; cursor += q + 1; } else { cursor += L; }
         }
       }
-      if (!__any_sync(0xffffffffu, myb >= 0)) break;
-      const bool has = myb >= 0;
-      const int t0 = has ? (myb << p.logB) : 0;
+      if (!__any_sync(0xffffffffu, myu >= 0)) break;
+      const bool has = myu >= 0;
+      const int us = has ? myu / nblk : cur_strip;
+      const int t0 = has ? ((myu - us * nblk) << p.logB) : 0;
+      if (multi && us != cur_strip) { cur_strip = us; wf.prepare(pd, us, prof_warp); }
+      const int row0 = cur_strip * S + g * R + 1;
       uint64_t mine = ~0ull;
-      wf.replay(pd, t0, has ? t0 + p.B : -1, p.B, [&](int k, int j, uint32_t e_new) {
+      wf.replay(pd, multi, t0, has ? t0 + p.B : -1, p.B, [&](int k, int j, uint32_t e_new) {
         if (((e_new ^ vmax2) & hmask) == 0) {
           const int i = row0 + k;
           if (i <= m && j >= 1 && j <= n) {
@@ -532,40 +602,50 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
 
     // ---- 3. traceback over a ring of recomputed columns ---------------------------------------------------
     // SWAligner::traceback, smithwaterman.cpp:40-78, literally: compare the three neighbours' VALUES.
+    // A session replays the strip that holds row ix into the ring; the row above a strip comes from the
+    // strip's boundary row in HBM.  Leaving the ring (to the left) or the strip (upwards) starts a new session.
     int ix = ie, iy = je;
     uint32_t len = 0, flags = 0, pos = 0;
     uint8_t* cx = tp.out_cx + (size_t)td.out * tp.cons_cap;
     uint8_t* cy = tp.out_cy + (size_t)td.out * tp.cons_cap;
     bool done = !active;
     while (!__all_sync(0xffffffffu, done)) {
-      const int l_e = (ix - 1) / R;
+      const int ss = (ix - 1) / S;                       // strip of row ix
+      const int il = ix - ss * S;                        // row within the strip, 1..S
+      const int l_e = (il - 1) / R;
       const int t_hi = done ? 0 : step_of<C>(iy, l_e);
-      int c_lo = iy - 2 - (ix + 8);      // restart at a checkpoint left of the columns the remaining rows can reach
+      int c_lo = iy - 2 - (il + 8);      // restart at a checkpoint left of the columns the remaining rows can reach
       if (c_lo < 0) c_lo = 0;
       const int t_lo = done ? 0 : (((c_lo / C) >> p.logB) << p.logB);
       const int valid_lo = max(C * t_lo, C * t_hi - tp.Wc + 1);     // oldest column every lane still holds
+      if (multi && !done && ss != cur_strip) { cur_strip = ss; wf.prepare(pd, ss, prof_warp); }
+      const int srow0 = g * R + 1;                       // first strip-local row of this lane
       if (!done && t_lo > 0) {
         // the checkpoint itself is column C * (t_lo - g) of this lane's rows
-        const uint32_t* ck = p.ckpt + pd.ck_off + (size_t)((t_lo >> p.logB) - 1) * state_words<R, C>() * L;
+        const uint32_t* ck = p.ckpt + pd.ck_off + wf.ck_index(pd, (t_lo >> p.logB) - 1);
         const int jc = C * (t_lo - g);
         if (jc >= 0) {
 #pragma unroll
-          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + row0 + k] = ck[k * L + g];
+          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + srow0 + k] = ck[k * L + g];
         }
       }
       const int nsteps = warp_max_i32(t_hi - t_lo);
-      wf.replay(pd, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
-        if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + row0 + k] = e_new;
+      wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
+        if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + srow0 + k] = e_new;
       });
       __syncwarp();
       if (g == 0 && !done) {
         // row 0 and column 0 of H are zero and never stored; stored words are packed E = H - G
+        const int row_lo = ss * S;                       // last row of the strip above (0 for strip 0)
+        const uint32_t* above = ss > 0 ? p.bnd + pd.bnd_off + (size_t)(ss - 1) * (n + 1) : nullptr;
         auto Hat = [&](int i, int j) -> int {
           if (i <= 0 || j <= 0) return 0;
-          return half_of(((volatile uint32_t*)scr)[(size_t)(j & wmask) * tp.rstride + i], half) + G;
+          if (i == row_lo) return half_of(((volatile const uint32_t*)above)[j], half) + G;
+          return half_of(((volatile uint32_t*)scr)[(size_t)(j & wmask) * tp.rstride + (i - row_lo)], half) + G;
         };
         while (true) {
-          if (iy - 1 < valid_lo && iy - 1 > 0) break;        // window exhausted: recompute further left
+          if (iy - 1 < valid_lo && iy - 1 > 0) break;        // ring exhausted: recompute further left
+          if (ix <= row_lo) break;                           // walked into the strip above
           const int n1 = Hat(ix - 1, iy - 1), n2 = Hat(ix, iy - 1), n3 = Hat(ix - 1, iy);
           if (len >= tp.cons_cap) { flags |= 1u; done = true; break; }
           if (n1 == 0 || n2 == 0 || n3 == 0) {
@@ -616,7 +696,7 @@ __global__ void task_max_kernel(const PairDesc* pairs, const TaskDesc* tasks, in
   const PairDesc pd = pairs[td.pair];
   const uint32_t* blk = blkmax + pd.blk_off;
   int v = -32768;
-  for (uint32_t w = 0; w < pd.nblk * (uint32_t)L; ++w) v = max(v, half_of(blk[w], td.half));
+  for (uint32_t w = 0; w < pd.nblk * pd.nstrips * (uint32_t)L; ++w) v = max(v, half_of(blk[w], td.half));
   const int m = td.half ? pd.mB : pd.mA;
   out[t] = (m == 0) ? -1 : max(v + G, 0);
 }

@@ -49,7 +49,7 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Geometry { int L = 0, logL = 0, R = 0; };
+struct Geometry { int L = 0, logL = 0, R = 0, nstrips = 1; };
 const int kRSet[] = {2, 4, 5, 8, 12, 16, 19, 24, 32};
 constexpr int kNumR = sizeof(kRSet) / sizeof(kRSet[0]);
 
@@ -60,7 +60,7 @@ struct LaunchClass {
   std::vector<TaskDesc> tasks;      // task id order: local_read * pieces + piece
   int pieces = 1;                   // tasks per read (1 = plain SWAligner)
   int nreads = 0;
-  size_t blk_words = 0, ck_words = 0, q_words = 0;
+  size_t blk_words = 0, ck_words = 0, q_words = 0, bnd_words = 0;
   int max_m = 0;
   // device copies
   DevBuf d_pairs, d_tasks;
@@ -101,7 +101,7 @@ struct swb_ctx {
   std::vector<uint64_t> offsets;
   std::vector<char> seq_host;       // kept for the custom-scoring re-alignment of the chunked path
   std::vector<LaunchClass> classes;
-  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_scratch, d_taskmax, d_winner;
+  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
   swb_stats stats{};
 };
@@ -240,15 +240,22 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
     const int need = ((int)kv.first + 31) / 32;
     for (int i = 0; i < kNumR && r_cap < need; ++i) if (kRSet[i] >= need) r_cap = kRSet[i];
     r_cap = std::min(r_cap, r_hard);
-    if (!choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g))
-      return fail(ctx, SWB_ERR_UNSUPPORTED, "sequence of " + std::to_string(kv.first) + " rows exceeds 32 lanes x " + std::to_string(r_hard) + " rows (long-sequence row striping is not built yet)");
+    if (!choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
+      // longer than one warp can hold: row strips of 32 x R rows, processed top to bottom by the same warp
+      int R = kRSet[0];
+      for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= r_hard) R = kRSet[i];
+      if (profile) { for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= std::max(r_pref, 8) && kRSet[i] <= r_hard) R = kRSet[i]; }
+      g.L = 32; g.logL = 5; g.R = R;
+      g.nstrips = ((int)kv.first + 32 * R - 1) / (32 * R);
+      if (ctx->C != 1) return fail(ctx, SWB_ERR_UNSUPPORTED, "row strips need SWB_COLS=1");
+    }
     geo_by_m[kv.first] = g;
   }
-  std::map<std::pair<int, int>, int> class_of;   // (L, R) -> class index
+  std::map<std::pair<int, int>, int> class_of;   // (L, R * 4096 + nstrips) -> class index
   std::vector<int> cls(seeds.size());
   for (size_t i = 0; i < seeds.size(); i += (size_t)pieces) {
     const Geometry g = geo_by_m[seeds[i].m];
-    auto key = std::make_pair(g.L, g.R);
+    auto key = std::make_pair(g.L, g.R * 4096 + g.nstrips);
     auto it = class_of.find(key);
     if (it == class_of.end()) { it = class_of.emplace(key, (int)out->size()).first; out->emplace_back(); out->back().geo = g; out->back().pieces = pieces; }
     for (int pc = 0; pc < pieces; ++pc) cls[i + pc] = it->second;
@@ -293,9 +300,12 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
         }
       }
       ++k;
-      pd.q_off = (uint32_t)lc.q_words; lc.q_words += (size_t)L * R;
-      pd.blk_off = lc.blk_words; lc.blk_words += (size_t)pd.nblk * L;
-      pd.ck_off = lc.ck_words; lc.ck_words += (size_t)pd.nblk * (R + ctx->C) * L;
+      const size_t ns = (size_t)lc.geo.nstrips;
+      pd.nstrips = (uint32_t)ns;
+      pd.q_off = (uint32_t)lc.q_words; lc.q_words += ns * L * R;
+      pd.blk_off = lc.blk_words; lc.blk_words += ns * pd.nblk * L;
+      pd.ck_off = lc.ck_words; lc.ck_words += ns * pd.nblk * (R + ctx->C) * L;
+      pd.bnd_off = lc.bnd_words; lc.bnd_words += (ns - 1) * ((size_t)pd.n + 1);
       lc.pairs.push_back(pd);
     }
     if (lc.q_words > 0xFFFFFFFFull) return fail(ctx, SWB_ERR_UNSUPPORTED, "batch too large for one launch class (split the batch)");
@@ -329,6 +339,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     CUDA_TRY(ctx->d_qpairs.ensure(lc.q_words * 4));
     CUDA_TRY(ctx->d_blkmax.ensure(lc.blk_words * 4));
     CUDA_TRY(ctx->d_ckpt.ensure(lc.ck_words * 4));
+    CUDA_TRY(ctx->d_bnd.ensure(lc.bnd_words * 4 + 256));
     PassParams pp{};
     pp.ref_raw = ctx->d_ref_raw.as<uint8_t>();
     pp.ref_code = ctx->d_ref_code.as<uint8_t>();
@@ -340,15 +351,17 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     pp.npairs = (int)lc.pairs.size();
     pp.blkmax = ctx->d_blkmax.as<uint32_t>();
     pp.ckpt = ctx->d_ckpt.as<uint32_t>();
+    pp.bnd = ctx->d_bnd.as<uint32_t>();
     pp.L = L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
     pp.sc = device_scoring(hs, force_default);
     if (profile) pp.sc.G = hs.G;
 
     // pack rows
     {
-      const long long total = (long long)lc.pairs.size() * L * R;
+      const int rows_per_pair = L * R * lc.geo.nstrips;
+      const long long total = (long long)lc.pairs.size() * rows_per_pair;
       const int thr = 256;
-      pack_rows_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.reads_raw, pp.pairs, pp.npairs, L * R, ctx->d_qpairs.as<uint32_t>());
+      pack_rows_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.reads_raw, pp.pairs, pp.npairs, rows_per_pair, ctx->d_qpairs.as<uint32_t>());
       CUDA_TRY(cudaGetLastError());
       ctx->stats.kernel_launches++;
     }
@@ -366,7 +379,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
       const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
       CUDA_TRY(launch_score(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
       ctx->stats.kernel_launches++;
-      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nblk * ctx->B * ctx->C * L * R * 2ull;
+      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nstrips * pd.nblk * ctx->B * ctx->C * L * R * 2ull;
     }
     if (!trace && !select_pieces) continue;
 
@@ -450,7 +463,7 @@ void swb_destroy(swb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   free_classes(ctx->classes);
-  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt,
+  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd,
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
                     &ctx->d_len, &ctx->d_flags}) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

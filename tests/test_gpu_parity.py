@@ -70,8 +70,8 @@ def test_c4_sample_golden(engine, pkg, c4_sample):
     """BASELINE config 4 shape: DB proteins (x) vs a 300-aa query (y), BLOSUM62 callback, gap 10."""
     engine.set_scoring_table(pkg.MODE_EXACT, synth.blosum62_table(), c4_sample["gap"])
     engine.set_reference(c4_sample["query"])
-    ents = [e for e in c4_sample["entries"] if len(e["x"]) <= 1024]  # TODO(strips): longer proteins need row striping
-    assert len(ents) > 140
+    ents = c4_sample["entries"]
+    assert max(len(e["x"]) for e in ents) > 1024       # exercises row strips (sequences longer than one warp holds)
     r = engine.align([e["x"] for e in ents], cons_stride=6000)
     for i, e in enumerate(ents):
         _check(r, i, e, tag="c4")
@@ -175,3 +175,39 @@ def test_cpp_shims_and_driver(tmp_path, data_small):
         for line, g in zip(rows[1:], want):
             f_ = line.split(", ")
             assert int(f_[-2]) == g["pos"] and float(f_[-1]) == g["score"]
+
+
+def test_long_sequences_row_strips(engine, pkg):
+    """Sequences longer than 32 lanes x 32 rows are cut into row strips (boundary rows in HBM).  Oracle parity
+    for both modes, incl. len(x) > len(y) and a traceback that crosses strip boundaries."""
+    rng = np.random.default_rng(21)
+    y = "".join(rng.choice(list("ACGT"), size=2600))
+    xs = []
+    for m, s0 in ((1025, 0), (1500, 700), (2047, 300), (2300, 100), (3100, 0)):
+        base = list((y * 2)[s0:s0 + m])
+        for q in range(m):
+            if rng.random() < 0.06:
+                base[q] = str(rng.choice(list("ACGT")))
+        xs.append("".join(base))
+    xs.append("".join(rng.choice(list("ACGT"), size=1300)))
+    for mode, omode, sc in ((pkg.MODE_SAT_U8, o.MODE_SAT_U8, (3, -3, 2)), (pkg.MODE_EXACT, o.MODE_EXACT, (3, -3, 2)), (pkg.MODE_EXACT, o.MODE_EXACT, (2, -3, 4))):
+        engine.set_scoring_match(mode, *sc)
+        engine.set_reference(y)
+        r = engine.align(xs, cons_stride=6000)
+        for i, x in enumerate(xs):
+            w = o.align(x, y, mode=omode, match=sc[0], mismatch=sc[1], gap=sc[2])
+            _check(r, i, w, tag=("strips", mode, sc, len(x)))
+            assert tuple(r["end"][i]) == w["end"]
+
+
+def test_long_pair_c5_shape(engine, pkg):
+    """BASELINE config 5 at the reference's own published shape (10 kbp read vs 30 kbp reference, py/eval.py:54),
+    EXACT semantics (omp_sw_solve_small.cpp:167) and SAT_U8 (MTSIMD, :164), against the oracle."""
+    ref = synth.c3_reference(30_000, seed=26)
+    reads = synth.mutated_reads(ref, 2, 10_000, seed=27, sub=0.02, ins=0.002, dele=0.002)
+    for mode, omode in ((pkg.MODE_EXACT, o.MODE_EXACT), (pkg.MODE_SAT_U8, o.MODE_SAT_U8)):
+        engine.set_scoring_match(mode, 3, -3, 2)
+        engine.set_reference(ref)
+        r = engine.align(reads, cons_stride=25_000)
+        for i, x in enumerate(reads):
+            _check(r, i, o.align(x, ref, mode=omode), tag=("c5", mode))
