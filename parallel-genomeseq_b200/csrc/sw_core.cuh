@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace swb {
 
@@ -101,7 +102,9 @@ struct LaneState {
   uint32_t bot[C];      // H - G of this lane's LAST row at each of the C columns of the previous step
                         // (bot[C-1] == E[R-1]); the lane below shuffles them in as its "north" inputs
 };
-template <int R, int C> __host__ __device__ constexpr int state_words() { return R + C; }   // E[R], up_prev, bot[0..C-2]
+// Checkpoint words per lane: E[R], up_prev, bot[0..C-2] = R + C registers.  In SAT_U8 mode every value is
+// E + G in [0, 255], so two registers (four bytes) share one word and the checkpoints take half the HBM.
+template <int R, int C, bool SAT> __host__ __device__ constexpr int state_words() { return SAT ? (R + C + 1) / 2 : R + C; }
 
 // Geometry of the skewed wavefront: at step t (1-based) lane g works on columns col_of(t,g,0..C-1).
 template <int C> __device__ __forceinline__ int col_of(int t, int g, int c) { return C * (t - g - 1) + 1 + c; }
@@ -166,15 +169,35 @@ struct NoHook {
   __device__ __forceinline__ void operator()(int, int, uint32_t) const {}
 };
 
-// y symbol for column j (1-based) of a pair's range, or the sentinel outside [1, n].
-template <bool PROFILE>
+// y symbol for column j (1-based) of a pair's range, or the sentinel outside [1, n].  MASKED = false skips the
+// range test (interior blocks of the score pass, where every lane's column is known to be inside the range).
+template <bool PROFILE, bool MASKED = true>
 __device__ __forceinline__ uint32_t load_y(const PassParams& p, const PairDesc& pd, int j) {
+  if (!MASKED) {
+    const uint32_t idx = pd.y_off + (uint32_t)(j - 1);
+    if (PROFILE) return __ldg(p.ref_code + idx);
+    return SYM_BASE | __ldg(p.ref_raw + idx);
+  }
   const bool in = (j >= 1) && (j <= (int)pd.n);
   const uint32_t idx = in ? (pd.y_off + (uint32_t)(j - 1)) : pd.y_off;
   if (PROFILE) { uint32_t c = __ldg(p.ref_code + idx); return in ? c : (uint32_t)(p.KP - 1); }
   uint32_t c = __ldg(p.ref_raw + idx);
   return in ? (SYM_BASE | c) : SENT_Y;
 }
+
+// Scores of one step held in registers (filled from the shared-memory profile one step ahead of their use).
+template <int R, int C>
+struct RegSelect {
+  uint32_t s[R][C];
+  __device__ __forceinline__ uint32_t operator()(int k, int c) const { return s[k][c]; }
+  template <class Sel>
+  __device__ __forceinline__ void fetch(const Sel& sel) {
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+      for (int c = 0; c < C; ++c) s[k][c] = sel(k, c);
+  }
+};
 
 template <int R, int C>
 __device__ __forceinline__ void init_state(LaneState<R, C>& st, const Scoring& sc) {
@@ -185,22 +208,44 @@ __device__ __forceinline__ void init_state(LaneState<R, C>& st, const Scoring& s
   for (int c = 0; c < C; ++c) st.bot[c] = sc.negG2;
 }
 
-// Checkpoint layout: word ((blk*(R+C) + k) * L + g); k == R holds up_prev, k > R the extra bot[] words.
+// Checkpoint layout: word ((unit * state_words + w) * L + g).  Register order: E[0..R-1], up_prev, bot[0..C-2].
 template <int R, int C>
-__device__ __forceinline__ void save_state(const LaneState<R, C>& st, uint32_t* ck, int L, int g) {
-#pragma unroll
-  for (int k = 0; k < R; ++k) ck[k * L + g] = st.E[k];
-  ck[R * L + g] = st.up_prev;
-#pragma unroll
-  for (int c = 0; c < C - 1; ++c) ck[(R + 1 + c) * L + g] = st.bot[c];
+__device__ __forceinline__ uint32_t state_reg(const LaneState<R, C>& st, int i) {
+  return i < R ? st.E[i] : (i == R ? st.up_prev : st.bot[i - R - 1]);
 }
-template <int R, int C>
-__device__ __forceinline__ void load_state(LaneState<R, C>& st, const uint32_t* ck, int L, int g) {
+template <int R, int C, bool SAT>
+__device__ __forceinline__ void save_state(const LaneState<R, C>& st, const Scoring& sc, uint32_t* ck, int L, int g) {
+  constexpr int N = R + C;
+  if (SAT) {
+    const uint32_t g2 = (uint32_t)sc.G * 0x00010001u;   // pack(+G, +G): E + G is in [0, 255]
 #pragma unroll
-  for (int k = 0; k < R; ++k) st.E[k] = ck[k * L + g];
-  st.up_prev = ck[R * L + g];
+    for (int w = 0; w < (N + 1) / 2; ++w) {
+      const uint32_t a = __vadd2(state_reg<R, C>(st, 2 * w), g2);
+      const uint32_t b = (2 * w + 1 < N) ? __vadd2(state_reg<R, C>(st, 2 * w + 1), g2) : 0u;
+      ck[w * L + g] = __byte_perm(a, b, 0x6420);   // bytes: a.lo, a.hi, b.lo, b.hi
+    }
+  } else {
 #pragma unroll
-  for (int c = 0; c < C - 1; ++c) st.bot[c] = ck[(R + 1 + c) * L + g];
+    for (int i = 0; i < N; ++i) ck[i * L + g] = state_reg<R, C>(st, i);
+  }
+}
+// value of checkpoint register i (packed E word) from a checkpoint
+template <int R, int C, bool SAT>
+__device__ __forceinline__ uint32_t ck_reg(const Scoring& sc, const uint32_t* ck, int L, int g, int i) {
+  if (SAT) {
+    const uint32_t w = ck[(i >> 1) * L + g];
+    const uint32_t v = (i & 1) ? __byte_perm(w, 0u, 0x4342) : __byte_perm(w, 0u, 0x4140);   // two bytes -> two u16 halves
+    return __vadd2(v, sc.negG2);
+  }
+  return ck[i * L + g];
+}
+template <int R, int C, bool SAT>
+__device__ __forceinline__ void load_state(LaneState<R, C>& st, const Scoring& sc, const uint32_t* ck, int L, int g) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) st.E[k] = ck_reg<R, C, SAT>(sc, ck, L, g, k);
+  st.up_prev = ck_reg<R, C, SAT>(sc, ck, L, g, R);
+#pragma unroll
+  for (int c = 0; c < C - 1; ++c) st.bot[c] = ck_reg<R, C, SAT>(sc, ck, L, g, R + 1 + c);
   st.bot[C - 1] = st.E[R - 1];
 }
 
@@ -250,7 +295,7 @@ struct Wavefront {
   __device__ __forceinline__ Wavefront(const PassParams& p_) : p(p_) {}
 
   __device__ __forceinline__ size_t blk_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * L; }
-  __device__ __forceinline__ size_t ck_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * state_words<R, C>() * L; }
+  __device__ __forceinline__ size_t ck_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * state_words<R, C, SAT>() * L; }
 
   // select the strip and load its rows (registers or shared-memory profile)
   __device__ __forceinline__ void prepare(const PairDesc& pd, int s, uint32_t* prof_warp) {
@@ -268,11 +313,27 @@ struct Wavefront {
   }
   __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
     if (t0 == 0) init_state<R, C>(st, p.sc);
-    else load_state<R, C>(st, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
+    else load_state<R, C, SAT>(st, p.sc, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
   }
   __device__ __forceinline__ void load_symbols(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
 #pragma unroll
     for (int c = 0; c < C; ++c) y[c] = load_y<PROFILE>(p, pd, col_of<C>(t, g, c));
+  }
+  template <bool MASKED>
+  __device__ __forceinline__ void load_symbols_m(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
+#pragma unroll
+    for (int c = 0; c < C; ++c) y[c] = load_y<PROFILE, MASKED>(p, pd, col_of<C>(t, g, c));
+  }
+  // one step with the scores supplied by `sel` (single-strip fast path of the score pass: no hook)
+  template <class Sel>
+  __device__ __forceinline__ void step_with(const Sel& sel, uint32_t& bmax) {
+    uint32_t upv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      upv[c] = __shfl_up_sync(0xffffffffu, st.bot[c], 1, L);
+      if (g == 0) upv[c] = p.sc.negG2;
+    }
+    step<R, C, SAT>(st, sel, p.sc, upv, bmax, NoHook());
   }
   // 32 boundary columns starting at column 32*k + 1, one per lane
   __device__ __forceinline__ uint32_t load_chunk(const PairDesc& pd, int k) const {
@@ -361,10 +422,77 @@ __device__ __forceinline__ void score_strip(Wavefront<R, C, SAT, PROFILE>& wf, c
       const int b = (t >> p.logB) - 1;
       if (live && b < (int)pd.nblk) {
         blk[wf.blk_index(pd, b) + g] = bmax;
-        save_state<R, C>(wf.st, ck + wf.ck_index(pd, b), L, g);
+        save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
       }
       bmax = NEG_INF2;
     }
+  }
+}
+
+// Single-strip score pass, software-pipelined: symbols are loaded two steps ahead and (profile select) the
+// scores of step t+1 are fetched from shared memory while step t computes.  Blocks whose columns (plus the
+// two-step look-ahead) are inside [1, n] for every lane of the warp skip the range tests.
+template <int R, int C, bool SAT, bool PROFILE>
+__device__ __forceinline__ void score_single(Wavefront<R, C, SAT, PROFILE>& wf, const PassParams& p, const PairDesc& pd,
+                                             int steps, int n_min, bool live) {
+  const int L = wf.L, g = wf.g;
+  uint32_t* blk = p.blkmax + pd.blk_off;
+  uint32_t* ck = p.ckpt + pd.ck_off;
+  wf.restore(pd, 0);
+  uint32_t bmax = NEG_INF2;
+  uint32_t y0[C], y1[C];               // symbols of steps t and t+1 (compare) / t+1 and t+2 (profile)
+  RegSelect<R, C> ra, rb;              // profile select: scores of the current / next step
+  if (PROFILE) {
+    wf.template load_symbols_m<true>(pd, 1, y0);
+#pragma unroll
+    for (int c = 0; c < C; ++c) wf.psel.set_column(c, y0[c]);
+    ra.fetch(wf.psel);
+    wf.template load_symbols_m<true>(pd, 2, y0);     // y0 = step t+1
+  } else {
+    wf.template load_symbols_m<true>(pd, 1, y0);     // y0 = step t
+    wf.template load_symbols_m<true>(pd, 2, y1);     // y1 = step t+1
+  }
+  const int nb = steps >> p.logB;
+  for (int b = 0; b < nb; ++b) {
+    const int t0 = b << p.logB;
+    const bool interior = (t0 + 1 >= L) && ((t0 + p.B + 2) * C <= n_min);
+    auto run = [&](auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      for (int t = t0 + 1; t <= t0 + p.B; t += 2) {
+        if (PROFILE) {
+          // step t (scores in ra); fetch scores of t+1 into rb; load symbols of t+2
+          wf.template load_symbols_m<MASKED>(pd, t + 2, y1);
+#pragma unroll
+          for (int c = 0; c < C; ++c) wf.psel.set_column(c, y0[c]);
+          rb.fetch(wf.psel);
+          wf.step_with(ra, bmax);
+          // step t+1 (scores in rb); fetch scores of t+2 into ra; load symbols of t+3
+          wf.template load_symbols_m<MASKED>(pd, t + 3, y0);
+#pragma unroll
+          for (int c = 0; c < C; ++c) wf.psel.set_column(c, y1[c]);
+          ra.fetch(wf.psel);
+          wf.step_with(rb, bmax);
+        } else {
+          uint32_t y2[C];
+          wf.template load_symbols_m<MASKED>(pd, t + 2, y2);
+#pragma unroll
+          for (int c = 0; c < C; ++c) wf.csel.set_column(c, y0[c]);
+          wf.step_with(wf.csel, bmax);
+          wf.template load_symbols_m<MASKED>(pd, t + 3, y0);
+#pragma unroll
+          for (int c = 0; c < C; ++c) wf.csel.set_column(c, y1[c]);
+          wf.step_with(wf.csel, bmax);
+#pragma unroll
+          for (int c = 0; c < C; ++c) { const uint32_t tmp = y0[c]; y0[c] = y2[c]; y1[c] = tmp; }
+        }
+      }
+    };
+    if (interior) run(std::false_type{}); else run(std::true_type{});
+    if (live && b < (int)pd.nblk) {
+      blk[wf.blk_index(pd, b) + g] = bmax;
+      save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
+    }
+    bmax = NEG_INF2;
   }
 }
 
@@ -397,8 +525,11 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
       __threadfence_block();
     }
   } else {
+    int n_min = (int)pd.n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_min = min(n_min, __shfl_xor_sync(0xffffffffu, n_min, o));
     wf.prepare(pd, 0, prof_warp);
-    score_strip<R, C, SAT, PROFILE, false>(wf, p, pd, steps, live);
+    score_single<R, C, SAT, PROFILE>(wf, p, pd, steps, n_min, live);
   }
 }
 
@@ -626,7 +757,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
         const int jc = C * (t_lo - g);
         if (jc >= 0) {
 #pragma unroll
-          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + srow0 + k] = ck[k * L + g];
+          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + srow0 + k] = ck_reg<R, C, SAT>(p.sc, ck, L, g, k);
         }
       }
       const int nsteps = warp_max_i32(t_hi - t_lo);

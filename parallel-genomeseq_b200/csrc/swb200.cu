@@ -304,7 +304,8 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       pd.nstrips = (uint32_t)ns;
       pd.q_off = (uint32_t)lc.q_words; lc.q_words += ns * L * R;
       pd.blk_off = lc.blk_words; lc.blk_words += ns * pd.nblk * L;
-      pd.ck_off = lc.ck_words; lc.ck_words += ns * pd.nblk * (R + ctx->C) * L;
+      const size_t ckw = ctx->sc.mode == SWB_MODE_SAT_U8 ? (size_t)(R + ctx->C + 1) / 2 : (size_t)(R + ctx->C);   // state_words<R, C, SAT>
+      pd.ck_off = lc.ck_words; lc.ck_words += ns * pd.nblk * ckw * L;
       pd.bnd_off = lc.bnd_words; lc.bnd_words += (ns - 1) * ((size_t)pd.n + 1);
       lc.pairs.push_back(pd);
     }
@@ -624,7 +625,7 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
   {
     size_t budget_mb = 8192;
     if (const char* e = getenv("SWB_CKPT_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
-    const double words_per_block = (double)((seeds.size() + 1) / 2) * ((double)max_m * 1.08 + 40.0);
+    const double words_per_block = (double)((seeds.size() + 1) / 2) * ((double)max_m * 1.08 + 40.0) * (hs.mode == SWB_MODE_SAT_U8 ? 0.5 : 1.0);
     int B = 32;
     ctx->C = 1;
     if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
