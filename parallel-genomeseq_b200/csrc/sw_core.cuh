@@ -41,7 +41,7 @@ struct PairDesc {
   uint32_t nblk;      // ceil((L - 1 + ceil(n / C)) / B) blocks of B steps
   uint32_t mA, mB;    // real row counts (0 = empty half)
   uint32_t xA, xB;    // byte offsets of the raw sequences in reads_raw
-  uint64_t blk_off;   // word offset into blkmax: nstrips * nblk * L words
+  uint64_t blk_off;   // word offset into blkmax: nstrips * nblk words (maximum over the L lanes of the group)
   uint64_t ck_off;    // word offset into ckpt  : nstrips * nblk * (R+C) * L words
   uint64_t bnd_off;   // word offset into bnd   : (nstrips-1) * (n+1) words (bottom row of every strip but the last)
   uint32_t nstrips;   // row strips of L*R rows (1 unless the sequences are longer than one warp can hold; then L == 32)
@@ -68,6 +68,12 @@ struct PassParams {
   uint32_t* blkmax;
   uint32_t* ckpt;
   uint32_t* bnd;               // strip boundary rows (packed E words), see PairDesc::bnd_off
+  // pipelined strips (few long pairs): one warp per (pair, strip) unit, strips of a pair run concurrently and
+  // hand their boundary rows over through HBM, synchronised by a per-unit progress counter
+  const uint2* units;          // (pair, strip) per warp, null = one warp per pair
+  int nunits;
+  uint32_t* progress;          // per unit: boundary columns published so far
+  uint32_t* abort_flag;        // set when a consumer gave up waiting (never expected; avoids a hang)
   int L, logL, B, logB;
   Scoring sc;
 };
@@ -274,6 +280,12 @@ __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassPar
   }
 }
 
+// maximum of a packed s16x2 word over the L lanes of a group (all 32 lanes call it)
+__device__ __forceinline__ uint32_t group_max_s16x2(uint32_t v, int L) {
+  for (int o = L >> 1; o > 0; o >>= 1) v = __vmaxs2(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 // Shared driver of both passes: restore (or initialise) the lane state, then run `nsteps` steps after
 // step t0.  All 32 lanes execute it together (full-mask shuffles); hook(k, j, E_new) fires for steps <= t1.
 //
@@ -292,9 +304,11 @@ struct Wavefront {
   const uint32_t* bnd_in = nullptr;   // boundary row above this strip (indexed by column), null for strip 0
   uint32_t* bnd_out = nullptr;        // boundary row below this strip, null for the last strip
   uint32_t chunk_cur = 0, chunk_next = 0;
+  volatile const uint32_t* wait_on = nullptr;   // progress counter of the strip above (pipelined strips)
+  uint32_t* publish_to = nullptr;               // this strip's progress counter
   __device__ __forceinline__ Wavefront(const PassParams& p_) : p(p_) {}
 
-  __device__ __forceinline__ size_t blk_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * L; }
+  __device__ __forceinline__ size_t blk_index(const PairDesc& pd, int b) const { return (size_t)strip * pd.nblk + b; }
   __device__ __forceinline__ size_t ck_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * state_words<R, C, SAT>() * L; }
 
   // select the strip and load its rows (registers or shared-memory profile)
@@ -338,7 +352,19 @@ struct Wavefront {
   // 32 boundary columns starting at column 32*k + 1, one per lane
   __device__ __forceinline__ uint32_t load_chunk(const PairDesc& pd, int k) const {
     const int j = 32 * k + 1 + lane;
-    return (bnd_in && j <= (int)pd.n) ? bnd_in[j] : p.sc.negG2;
+    if (wait_on && bnd_in) {
+      // pipelined strips: wait until the strip above has published the last column of this chunk
+      const uint32_t need = (uint32_t)min((int)pd.n, 32 * k + 32);
+      if (32 * k + 1 <= (int)pd.n) {
+        unsigned spins = 0;
+        while (*wait_on < need) {
+          __nanosleep(400);
+          if (++spins > (1u << 24)) { if (p.abort_flag) *p.abort_flag = 1u; break; }
+        }
+        __threadfence();
+      }
+    }
+    return (bnd_in && j <= (int)pd.n) ? ((volatile const uint32_t*)bnd_in)[j] : p.sc.negG2;
   }
   template <bool BND, class Hook>
   __device__ __forceinline__ void one_step(const PairDesc& pd, int t, const uint32_t (&ycur)[C], uint32_t& bmax, Hook&& hook) {
@@ -367,7 +393,10 @@ struct Wavefront {
     }
     if (BND) {
       const int j = col_of<C>(t, g, 0);
-      if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) bnd_out[j] = st.bot[0];
+      if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) {
+        bnd_out[j] = st.bot[0];
+        if (publish_to && ((j & 127) == 0 || j == (int)pd.n)) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)j; }
+      }
     }
   }
   template <bool BND>
@@ -420,8 +449,9 @@ __device__ __forceinline__ void score_strip(Wavefront<R, C, SAT, PROFILE>& wf, c
     wf.template one_step<BND>(pd, t, ycur, bmax, [](int, int, uint32_t) {});
     if ((t & (p.B - 1)) == 0) {
       const int b = (t >> p.logB) - 1;
+      const uint32_t gm = group_max_s16x2(bmax, L);
       if (live && b < (int)pd.nblk) {
-        blk[wf.blk_index(pd, b) + g] = bmax;
+        if (g == 0) blk[wf.blk_index(pd, b)] = gm;
         save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
       }
       bmax = NEG_INF2;
@@ -488,8 +518,9 @@ __device__ __forceinline__ void score_single(Wavefront<R, C, SAT, PROFILE>& wf, 
       }
     };
     if (interior) run(std::false_type{}); else run(std::true_type{});
+    const uint32_t gm = group_max_s16x2(bmax, L);
     if (live && b < (int)pd.nblk) {
-      blk[wf.blk_index(pd, b) + g] = bmax;
+      if (g == 0) blk[wf.blk_index(pd, b)] = gm;
       save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
     }
     bmax = NEG_INF2;
@@ -505,6 +536,21 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   const int L = p.L;
   const int g = lane & (L - 1);
   const int groups_per_warp = 32 >> p.logL;
+  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+  if (C == 1 && p.units) {
+    // pipelined strips: this warp owns ONE strip of one pair.  Producers have lower unit indices than their
+    // consumers, and thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
+    if (gwarp >= p.nunits) return;
+    const uint2 u = p.units[gwarp];
+    const PairDesc pd = p.pairs[u.x];
+    Wavefront<R, C, SAT, PROFILE> wf(p);
+    wf.L = L; wf.g = g; wf.lane = lane;
+    wf.prepare(pd, (int)u.y, prof_warp);
+    wf.wait_on = u.y > 0 ? p.progress + (gwarp - 1) : nullptr;
+    wf.publish_to = (u.y + 1 < pd.nstrips) ? p.progress + gwarp : nullptr;
+    score_strip<R, C, SAT, PROFILE, true>(wf, p, pd, (int)pd.nblk << p.logB, true);
+    return;
+  }
   int pair = gwarp * groups_per_warp + (lane >> p.logL);
   const bool live = pair < p.npairs;
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
@@ -512,7 +558,6 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
 
   Wavefront<R, C, SAT, PROFILE> wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
-  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
 
   // run whole blocks so that every lane flushes together; lanes past their range see sentinel columns
   const int steps = warp_max_i32((int)pd.nblk << p.logB);
@@ -636,7 +681,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
     // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------------
     const uint32_t* blk = p.blkmax + pd.blk_off;
     int vmax = -32768;
-    for (uint32_t w = g; w < (uint32_t)nunits * (uint32_t)L; w += L) vmax = max(vmax, half_of(blk[w], half));
+    for (int w = g; w < nunits; w += L) vmax = max(vmax, half_of(blk[w], half));
     vmax = group_max_i32(vmax, L);
     const int score = vmax + G;
     if (active && (m == 0 || score <= 0)) {
@@ -670,9 +715,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
           const int phase = pos >= nunits;
           u = pos - phase * nunits;
           const int us = u / nblk, ub = u - us * nblk;
-          int bm = -32768;
-          for (int q = 0; q < L; ++q) bm = max(bm, half_of(blk[(size_t)u * L + q], half));
-          if (bm == vmax) {
+          if (half_of(blk[u], half) == vmax) {
             const int t0 = ub << p.logB;
             const int jmin = max(1, C * (t0 - (L - 1)) + 1), jmax = min(n, C * (t0 + p.B));
             const int imin = us * S + 1, imax = min(m, (us + 1) * S);
@@ -807,12 +850,13 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
 // Small helper kernels
 // ======================================================================================================
 // qpairs[q_off + row] = pack(symA(row), symB(row)); rows beyond a half's length hold SENT_X.
-__global__ void pack_rows_kernel(const uint8_t* reads_raw, const PairDesc* pairs, int npairs, int rows_per_pair, uint32_t* qpairs) {
+__global__ void pack_rows_kernel(const uint8_t* reads_raw, const PairDesc* pairs, int npairs, int max_rows_per_pair, int rows_per_strip, uint32_t* qpairs) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)npairs * rows_per_pair;
+  const long long total = (long long)npairs * max_rows_per_pair;
   if (idx >= total) return;
-  const int pair = (int)(idx / rows_per_pair), row = (int)(idx % rows_per_pair);
+  const int pair = (int)(idx / max_rows_per_pair), row = (int)(idx % max_rows_per_pair);
   const PairDesc pd = pairs[pair];
+  if (row >= (int)pd.nstrips * rows_per_strip) return;
   const uint32_t a = row < (int)pd.mA ? (SYM_BASE | reads_raw[pd.xA + row]) : SENT_X;
   const uint32_t b = row < (int)pd.mB ? (SYM_BASE | reads_raw[pd.xB + row]) : SENT_X;
   qpairs[pd.q_off + row] = a | (b << 16);
@@ -820,14 +864,14 @@ __global__ void pack_rows_kernel(const uint8_t* reads_raw, const PairDesc* pairs
 
 // Per-task maximum (E-space + G = score) from the block maxima; used by the chunked path to pick the
 // best piece (plocalaligner.cpp:122-129) before any traceback.
-__global__ void task_max_kernel(const PairDesc* pairs, const TaskDesc* tasks, int ntasks, const uint32_t* blkmax, int L, int G, int32_t* out) {
+__global__ void task_max_kernel(const PairDesc* pairs, const TaskDesc* tasks, int ntasks, const uint32_t* blkmax, int G, int32_t* out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntasks) return;
   const TaskDesc td = tasks[t];
   const PairDesc pd = pairs[td.pair];
   const uint32_t* blk = blkmax + pd.blk_off;
   int v = -32768;
-  for (uint32_t w = 0; w < pd.nblk * pd.nstrips * (uint32_t)L; ++w) v = max(v, half_of(blk[w], td.half));
+  for (uint32_t w = 0; w < pd.nblk * pd.nstrips; ++w) v = max(v, half_of(blk[w], td.half));
   const int m = td.half ? pd.mB : pd.mA;
   out[t] = (m == 0) ? -1 : max(v + G, 0);
 }

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <numeric>
 #include <string>
@@ -61,7 +62,7 @@ struct LaunchClass {
   int pieces = 1;                   // tasks per read (1 = plain SWAligner)
   int nreads = 0;
   size_t blk_words = 0, ck_words = 0, q_words = 0, bnd_words = 0;
-  int max_m = 0;
+  int max_m = 0, max_strips = 1;
   // device copies
   DevBuf d_pairs, d_tasks;
 };
@@ -101,7 +102,7 @@ struct swb_ctx {
   std::vector<uint64_t> offsets;
   std::vector<char> seq_host;       // kept for the custom-scoring re-alignment of the chunked path
   std::vector<LaunchClass> classes;
-  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner;
+  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
   swb_stats stats{};
 };
@@ -118,6 +119,20 @@ namespace {
   } while (0)
 
 int fail(swb_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+// SWB_DEBUG=1: synchronise after every kernel and print its wall time (diagnostics only; distorts timings)
+struct DebugTimer {
+  bool on; cudaStream_t st; double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit DebugTimer(cudaStream_t s) : on(getenv("SWB_DEBUG") != nullptr), st(s), t0(0) { if (on) { cudaStreamSynchronize(st); t0 = now(); } }
+  void mark(const char* what, int L, int R, size_t n) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const double t1 = now();
+    fprintf(stderr, "[swb200] %-14s L=%-2d R=%-2d items=%-8zu %9.3f ms\n", what, L, R, n, t1 - t0);
+    t0 = t1;
+  }
+};
 
 // Symbol-score selection of the kernels: "profile" = per-warp query profile in shared memory (one LDS per
 // cell pair, any scoring table), "compare" = HSET2 + LOP3 on packed symbols (match/mismatch scoring only).
@@ -234,28 +249,49 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
   std::map<uint32_t, size_t> count_by_m;
   for (auto& s : seeds) count_by_m[s.m]++;
   std::map<uint32_t, Geometry> geo_by_m;
+  int r_strip = kRSet[0];            // rows per lane of the strip geometry (L = 32)
+  {
+    int cap = profile ? r_pref : 32;
+    for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= cap) r_strip = kRSet[i];
+    // few long pairs (the long-pair config): the strips of a pair run concurrently, one warp each, so prefer
+    // thin strips — as thin as the HBM budget for the boundary rows allows — to put a warp on every SM sub-partition
+    uint32_t m_max = 0, n_max = 0;
+    for (auto& sd : seeds) { m_max = std::max(m_max, sd.m); n_max = std::max(n_max, sd.n); }
+    const size_t npairs_est = (seeds.size() + 1) / 2;
+    if (npairs_est < 148 * 8 && (int)m_max > 32 * r_strip) {
+      size_t budget_mb = 32768;
+      if (const char* e = getenv("SWB_BND_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
+      for (int i = kNumR - 1; i >= 0; --i) {
+        const int R = kRSet[i];
+        if (R > r_strip || R < 4) continue;
+        const double strips = std::ceil((double)m_max / (32.0 * R));
+        const double bytes = (strips - 1) * ((double)n_max + 1) * 4.0 * (double)npairs_est;
+        if (bytes > (double)budget_mb * 1048576.0) break;
+        r_strip = R;
+        if (strips * (double)npairs_est >= 148.0 * 4.0) break;      // one warp per SM sub-partition is enough
+      }
+    }
+    if (const char* e = getenv("SWB_STRIP_R")) {
+      const int want = std::max(2, std::min(r_hard, atoi(e)));
+      for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= want) r_strip = kRSet[i];
+    }
+  }
   for (auto& kv : count_by_m) {
     Geometry g;
-    int r_cap = r_pref;
-    const int need = ((int)kv.first + 31) / 32;
-    for (int i = 0; i < kNumR && r_cap < need; ++i) if (kRSet[i] >= need) r_cap = kRSet[i];
-    r_cap = std::min(r_cap, r_hard);
-    if (!choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
-      // longer than one warp can hold: row strips of 32 x R rows, processed top to bottom by the same warp
-      int R = kRSet[0];
-      for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= r_hard) R = kRSet[i];
-      if (profile) { for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= std::max(r_pref, 8) && kRSet[i] <= r_hard) R = kRSet[i]; }
-      g.L = 32; g.logL = 5; g.R = R;
-      g.nstrips = ((int)kv.first + 32 * R - 1) / (32 * R);
+    const int r_cap = profile ? std::max(r_pref, kRSet[0]) : 32;
+    if ((int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
+      // longer than one warp holds at the preferred rows-per-lane: row strips of 32 x R rows, processed top
+      // to bottom (the strip count is per pair, so one launch class serves every length)
+      g.L = 32; g.logL = 5; g.R = r_strip; g.nstrips = 0;     // 0 = "per pair"
       if (ctx->C != 1) return fail(ctx, SWB_ERR_UNSUPPORTED, "row strips need SWB_COLS=1");
     }
     geo_by_m[kv.first] = g;
   }
-  std::map<std::pair<int, int>, int> class_of;   // (L, R * 4096 + nstrips) -> class index
+  std::map<std::pair<int, int>, int> class_of;   // (L, R) -> class index
   std::vector<int> cls(seeds.size());
   for (size_t i = 0; i < seeds.size(); i += (size_t)pieces) {
     const Geometry g = geo_by_m[seeds[i].m];
-    auto key = std::make_pair(g.L, g.R * 4096 + g.nstrips);
+    auto key = std::make_pair(g.L, g.R);
     auto it = class_of.find(key);
     if (it == class_of.end()) { it = class_of.emplace(key, (int)out->size()).first; out->emplace_back(); out->back().geo = g; out->back().pieces = pieces; }
     for (int pc = 0; pc < pieces; ++pc) cls[i + pc] = it->second;
@@ -272,13 +308,17 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
     // pairing order: by (y_off, n), then id — tasks of one pair must share the y-range
     std::vector<uint32_t> order(id.size());
     std::iota(order.begin(), order.end(), 0u);
-    bool uniform = true;
-    for (size_t k = 1; k < id.size() && uniform; ++k) uniform = seeds[id[k]].y_off == seeds[id[0]].y_off && seeds[id[k]].n == seeds[id[0]].n;
-    if (!uniform)
+    bool uniform = true, same_m = true;
+    for (size_t k = 1; k < id.size() && (uniform || same_m); ++k) {
+      uniform = uniform && seeds[id[k]].y_off == seeds[id[0]].y_off && seeds[id[k]].n == seeds[id[0]].n;
+      same_m = same_m && seeds[id[k]].m == seeds[id[0]].m;
+    }
+    if (!uniform || (!same_m && L == 32))
       std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         const TaskSeed &sa = seeds[id[a]], &sb = seeds[id[b]];
         if (sa.y_off != sb.y_off) return sa.y_off < sb.y_off;
-        return sa.n < sb.n;
+        if (sa.n != sb.n) return sa.n < sb.n;
+        return L == 32 && sa.m > sb.m;       // longest first: pair-mates of similar length, big work units scheduled first
       });
     size_t k = 0;
     while (k < order.size()) {
@@ -300,10 +340,11 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
         }
       }
       ++k;
-      const size_t ns = (size_t)lc.geo.nstrips;
+      const size_t ns = (L == 32) ? ((size_t)std::max(pd.mA, pd.mB) + (size_t)L * R - 1) / ((size_t)L * R) : 1;
       pd.nstrips = (uint32_t)ns;
+      lc.max_strips = std::max(lc.max_strips, (int)ns);
       pd.q_off = (uint32_t)lc.q_words; lc.q_words += ns * L * R;
-      pd.blk_off = lc.blk_words; lc.blk_words += ns * pd.nblk * L;
+      pd.blk_off = lc.blk_words; lc.blk_words += ns * pd.nblk;
       const size_t ckw = ctx->sc.mode == SWB_MODE_SAT_U8 ? (size_t)(R + ctx->C + 1) / 2 : (size_t)(R + ctx->C);   // state_words<R, C, SAT>
       pd.ck_off = lc.ck_words; lc.ck_words += ns * pd.nblk * ckw * L;
       pd.bnd_off = lc.bnd_words; lc.bnd_words += (ns - 1) * ((size_t)pd.n + 1);
@@ -334,6 +375,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
   const HostScoring& hs = ctx->sc;
   const bool sat = hs.mode == SWB_MODE_SAT_U8;
   const bool profile = use_profile(ctx, force_default);
+  DebugTimer dbg(ctx->stream);
   for (size_t ci = 0; ci < nclasses; ++ci) {
     LaunchClass& lc = classes[ci];
     const int L = lc.geo.L, R = lc.geo.R;
@@ -359,10 +401,10 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
 
     // pack rows
     {
-      const int rows_per_pair = L * R * lc.geo.nstrips;
+      const int rows_per_pair = L * R * lc.max_strips;
       const long long total = (long long)lc.pairs.size() * rows_per_pair;
       const int thr = 256;
-      pack_rows_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.reads_raw, pp.pairs, pp.npairs, rows_per_pair, ctx->d_qpairs.as<uint32_t>());
+      pack_rows_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.reads_raw, pp.pairs, pp.npairs, rows_per_pair, L * R, ctx->d_qpairs.as<uint32_t>());
       CUDA_TRY(cudaGetLastError());
       ctx->stats.kernel_launches++;
     }
@@ -376,11 +418,43 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     }
     const int groups_per_warp = 32 / L;
     {
-      const size_t warps = (lc.pairs.size() + groups_per_warp - 1) / groups_per_warp;
+      size_t warps = (lc.pairs.size() + groups_per_warp - 1) / groups_per_warp;
+      // few long pairs: run the strips of a pair concurrently, one warp per (pair, strip) unit
+      size_t total_units = 0;
+      for (auto& pd : lc.pairs) total_units += pd.nstrips;
+      const bool pipelined = L == 32 && lc.max_strips > 1 && ctx->C == 1 && lc.pairs.size() < 148 * 8 && !getenv("SWB_NO_PIPELINE");
+      pp.units = nullptr; pp.nunits = 0; pp.progress = nullptr; pp.abort_flag = nullptr;
+      if (pipelined) {
+        std::vector<uint2> units;
+        units.reserve(total_units);
+        for (size_t pi = 0; pi < lc.pairs.size(); ++pi)
+          for (uint32_t st = 0; st < lc.pairs[pi].nstrips; ++st) units.push_back(make_uint2((unsigned)pi, st));
+        CUDA_TRY(ctx->d_units.ensure(units.size() * sizeof(uint2)));
+        CUDA_TRY(ctx->d_progress.ensure((units.size() + 1) * 4));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_units.p, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_progress.p, 0, (units.size() + 1) * 4, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));      // `units` is a host temporary
+        pp.units = ctx->d_units.as<uint2>(); pp.nunits = (int)units.size();
+        pp.progress = ctx->d_progress.as<uint32_t>();
+        pp.abort_flag = ctx->d_progress.as<uint32_t>() + units.size();
+        warps = units.size();
+        warps_per_cta = 1;                                   // spread the units over all SMs
+        if (profile) smem = (size_t)ctx->KP * R * 32 * 4;
+      }
       const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
       CUDA_TRY(launch_score(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
       ctx->stats.kernel_launches++;
+      dbg.mark("score", L, R, lc.pairs.size());
       for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nstrips * pd.nblk * ctx->B * ctx->C * L * R * 2ull;
+      if (pipelined) {
+        uint32_t aborted = 0;
+        CUDA_TRY(cudaMemcpyAsync(&aborted, pp.abort_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (aborted) return fail(ctx, SWB_ERR_CUDA, "pipelined strips: a strip timed out waiting for its producer");
+        pp.units = nullptr; pp.nunits = 0;
+        warps_per_cta = 4;
+        if (profile) { const size_t per_warp = (size_t)ctx->KP * R * 32 * 4; while (warps_per_cta > 1 && per_warp * warps_per_cta > 200 * 1024) warps_per_cta >>= 1; smem = per_warp * warps_per_cta; }
+      }
     }
     if (!trace && !select_pieces) continue;
 
@@ -390,7 +464,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
       CUDA_TRY(ctx->d_taskmax.ensure(lc.tasks.size() * 4));
       CUDA_TRY(ctx->d_winner.ensure((size_t)lc.nreads * 4));
       const int thr = 128;
-      task_max_kernel<<<(unsigned)((lc.tasks.size() + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.pairs, lc.d_tasks.as<TaskDesc>(), (int)lc.tasks.size(), pp.blkmax, L, pp.sc.G, ctx->d_taskmax.as<int32_t>());
+      task_max_kernel<<<(unsigned)((lc.tasks.size() + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.pairs, lc.d_tasks.as<TaskDesc>(), (int)lc.tasks.size(), pp.blkmax, pp.sc.G, ctx->d_taskmax.as<int32_t>());
       CUDA_TRY(cudaGetLastError());
       select_piece_kernel<<<(unsigned)((lc.nreads + thr - 1) / thr), thr, 0, ctx->stream>>>(ctx->d_taskmax.as<int32_t>(), lc.nreads, lc.pieces, ctx->d_winner.as<uint32_t>());
       CUDA_TRY(cudaGetLastError());
@@ -432,6 +506,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     CUDA_TRY(launch_trace(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
     CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->stats.kernel_launches++;
+    dbg.mark("trace", L, R, (size_t)ntrace);
     ctx->stats.cells_pass2 += (uint64_t)ntrace * (uint64_t)(3 * ctx->B * ctx->C + lc.max_m + 16) * L * R * 2ull;
     ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
   }
@@ -464,7 +539,7 @@ void swb_destroy(swb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   free_classes(ctx->classes);
-  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd,
+  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd, &ctx->d_units, &ctx->d_progress,
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
                     &ctx->d_len, &ctx->d_flags}) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
