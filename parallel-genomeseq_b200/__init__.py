@@ -178,6 +178,15 @@ class Engine:
         self._check(self.lib.swb_last_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
+    def matrix(self, x):
+        """Dense H, (len(x)+1) x (len(reference)+1) int32 — Abstract_Similarity_Matrix::operator()(row, col)
+        (similaritymatrix.h:13-24) through the device path; tests and small inputs only."""
+        xb = x.encode("latin-1") if isinstance(x, str) else bytes(x)
+        n = len(self._ref_keepalive)
+        out = np.zeros((len(xb) + 1, n + 1), np.int32)
+        self._check(self.lib.swb_matrix(self.h, xb, len(xb), out.ctypes.data))
+        return out
+
     # ---- one-call API (host buffers in, host buffers out) ----------------------------------------------
     def align(self, seqs, npiece=0, ratio=0.0, consensus=True, cons_stride=None):
         """Returns dict(score, pos, end, len, flags, cx, cy, device_us); cx/cy are lists of str (end -> start)."""

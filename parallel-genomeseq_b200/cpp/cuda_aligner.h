@@ -154,13 +154,16 @@ class CUDA_Similarity_Matrix_Tag {
     if (dense_.empty()) {
       dense_.resize((x_.size() + 1) * (y_.size() + 1));
       Context& c = Context::instance();
+      if (apply_scoring_) apply_scoring_(c); else c.set_scoring_match(MODE, 3.0f, -3.0f, 2.0f);
       c.set_reference(y_);
       c.check(swb_matrix(c.raw(), x_.data(), x_.size(), dense_.data()));
     }
     return (float)dense_[(size_t)row * (y_.size() + 1) + (size_t)col];
   }
  private:
+  template <class> friend class CUDASWAligner;
   std::string_view x_, y_;
+  std::function<void(Context&)> apply_scoring_;   // set by the owning aligner: its callback + gap
   mutable std::vector<int32_t> dense_;
 };
 using CUDA_Similarity_Matrix_Skewed = CUDA_Similarity_Matrix_Tag<SWB_MODE_SAT_U8>;
@@ -212,12 +215,16 @@ class CUDASWAligner : public LocalAligner<SMT> {
   unsigned int getPos() const override { return r_.pos; }
   std::string_view getConsensus_x() const override { return r_.cx; }
   std::string_view getConsensus_y() const override { return r_.cy; }
-  const SMT& getSimilarity_matrix() const override { return sm_; }
+  const SMT& getSimilarity_matrix() const override {
+    const detail::Scoring* sc = &sc_;
+    sm_.apply_scoring_ = [sc](Context& c) { sc->apply(c, SMT::mode); };
+    return sm_;
+  }
   TimingsVec getTimings() const override { return make_timings(r_.device_us, r_.device_us); }
 
  private:
   std::string_view x_, y_;
-  SMT sm_;
+  mutable SMT sm_;
   detail::Scoring sc_;
   detail::Result r_;
 };

@@ -845,6 +845,41 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
   }
 }
 
+// ======================================================================================================
+// Dense H for one pair (tests / small inputs): the Abstract_Similarity_Matrix::operator()(row, col) surface.
+// One warp replays every strip from its initial state and stores H = E + G of half A, row-major (m+1) x (n+1).
+// ======================================================================================================
+struct DumpParams {
+  PassParams pp;
+  int32_t* out;     // (m+1) x (n+1), pre-zeroed
+  int m, n;
+};
+
+template <int R, int C, bool SAT, bool PROFILE>
+__global__ void __launch_bounds__(128) dump_kernel(const DumpParams dp) {
+  extern __shared__ uint32_t smem_prof[];
+  const PassParams& p = dp.pp;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32 || blockIdx.x > 0) return;
+  const int L = p.L;                       // the host stages a single pair with L == 32
+  const int g = lane & (L - 1);
+  const PairDesc pd = p.pairs[0];
+  Wavefront<R, C, SAT, PROFILE> wf(p);
+  wf.L = L; wf.g = g; wf.lane = lane;
+  const int S = L * R;
+  const int steps = (int)pd.nblk << p.logB;
+  const bool multi = pd.nstrips > 1;
+  for (int s = 0; s < (int)pd.nstrips; ++s) {
+    wf.prepare(pd, s, smem_prof);
+    const int row0 = s * S + g * R + 1;
+    wf.replay(pd, multi, 0, steps, steps, [&](int k, int j, uint32_t e_new) {
+      const int i = row0 + k;
+      if (i <= dp.m && j >= 1 && j <= dp.n) dp.out[(size_t)i * (dp.n + 1) + j] = half_of(e_new, 0) + p.sc.G;
+    });
+    __syncwarp();
+  }
+}
+
 #ifdef SWB_HELPER_KERNELS
 // ======================================================================================================
 // Small helper kernels

@@ -30,8 +30,16 @@ cudaError_t trace_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, 
   if (profile) return sat ? go(trace_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
   return sat ? go(trace_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(trace_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
 }
+template <int C>
+cudaError_t dump_c(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
+  if (profile) return sat ? go(dump_kernel<SWB_R, C, true, true>, dim3(1), dim3(32), smem, st, p) : go(dump_kernel<SWB_R, C, false, true>, dim3(1), dim3(32), smem, st, p);
+  return sat ? go(dump_kernel<SWB_R, C, true, false>, dim3(1), dim3(32), 0, st, p) : go(dump_kernel<SWB_R, C, false, false>, dim3(1), dim3(32), 0, st, p);
+}
 }  // namespace
 
+cudaError_t SWB_CAT(swb_launch_dump_r, SWB_R)(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
+  return dump_c<1>(sat, profile, smem, st, p);
+}
 cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
   return C == 1 ? score_c<1>(sat, profile, grid, block, smem, st, p) : score_c<2>(sat, profile, grid, block, smem, st, p);
 }

@@ -29,7 +29,8 @@ using namespace swb;
 // one translation unit per rows-per-lane value R (csrc/sw_inst.cu compiled with -DSWB_R=<R>)
 #define SWB_DECL(RR)                                                                                                  \
   cudaError_t swb_launch_score_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p); \
-  cudaError_t swb_launch_trace_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p);
+  cudaError_t swb_launch_trace_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p); \
+  cudaError_t swb_launch_dump_r##RR(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p);
 SWB_DECL(2) SWB_DECL(4) SWB_DECL(5) SWB_DECL(8) SWB_DECL(12) SWB_DECL(16) SWB_DECL(19) SWB_DECL(24) SWB_DECL(32)
 #undef SWB_DECL
 
@@ -98,6 +99,7 @@ struct swb_ctx {
   unsigned flags = 0;
   size_t cons_stride = 0;
   int B = 64, logB = 6;
+  bool force_l32 = false;           // swb_matrix: always the 32-lane geometry (one pair per warp)
   int C = 1;                        // columns per wavefront step (2 = more ILP per warp; measured slower on B200, kept selectable)
   std::vector<uint64_t> offsets;
   std::vector<char> seq_host;       // kept for the custom-scoring re-alignment of the chunked path
@@ -209,6 +211,15 @@ cudaError_t launch_trace(int R, int C, bool sat, bool profile, dim3 grid, dim3 b
   }
 }
 
+cudaError_t launch_dump(int R, bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
+  switch (R) {
+#define SWB_CASE(RR) case RR: return swb_launch_dump_r##RR(sat, profile, smem, st, p);
+    SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
+#undef SWB_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // Upload the (s + G) table of the profile select: [257][KP] int16, row 256 / column KP-1 = sentinels.
 int upload_profile_table(swb_ctx* ctx) {
   if (!ctx->table_dirty) return SWB_OK;
@@ -279,7 +290,7 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
   for (auto& kv : count_by_m) {
     Geometry g;
     const int r_cap = profile ? std::max(r_pref, kRSet[0]) : 32;
-    if ((int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
+    if (ctx->force_l32 || (int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
       // longer than one warp holds at the preferred rows-per-lane: row strips of 32 x R rows, processed top
       // to bottom (the strip count is per pair, so one launch class serves every length)
       g.L = 32; g.logL = 5; g.R = r_strip; g.nstrips = 0;     // 0 = "per pair"
@@ -827,8 +838,45 @@ int swb_last_stats(const swb_ctx* ctx, swb_stats* out) {
 }
 
 int swb_matrix(swb_ctx* ctx, const char* x, size_t m, int32_t* out) {
-  (void)x; (void)m; (void)out;
-  return fail(ctx, SWB_ERR_UNSUPPORTED, "swb_matrix is not built yet");
+  // Dense H through the device path: stage the single sequence (L = 32 geometry, strips as needed), run the
+  // score pass once (it writes the strip boundary rows the replay reads), then replay with a store hook.
+  if (!ctx || !x || !out || m == 0) return SWB_ERR_ARG;
+  if (ctx->y.empty()) return fail(ctx, SWB_ERR_STATE, "swb_set_reference has not been called");
+  const size_t n = ctx->y.size();
+  if ((m + 1) * (n + 1) > ((size_t)1 << 28)) return fail(ctx, SWB_ERR_UNSUPPORTED, "swb_matrix is for small inputs: (m+1)*(n+1) must not exceed 2^28 cells");
+  const uint64_t offs[2] = {0, m};
+  ctx->force_l32 = true;
+  int rc = swb_batch_stage(ctx, x, offs, 1, 0, 0.f, 0, 0);
+  ctx->force_l32 = false;
+  if (rc) return rc;
+  rc = swb_batch_run(ctx, nullptr);
+  if (rc) return rc;
+  LaunchClass& lc = ctx->classes[0];
+  if (lc.geo.L != 32) {
+    // re-stage with the strip geometry forced to 32 lanes: cheap, the input is small
+    return fail(ctx, SWB_ERR_UNSUPPORTED, "internal: swb_matrix expects the 32-lane geometry");
+  }
+  DevBuf d_out;
+  CUDA_TRY(d_out.ensure((m + 1) * (n + 1) * sizeof(int32_t)));
+  CUDA_TRY(cudaMemsetAsync(d_out.p, 0, (m + 1) * (n + 1) * sizeof(int32_t), ctx->stream));
+  const bool sat = ctx->sc.mode == SWB_MODE_SAT_U8;
+  const bool profile = use_profile(ctx, false);
+  DumpParams dp{};
+  PassParams& pp = dp.pp;
+  pp.ref_raw = ctx->d_ref_raw.as<uint8_t>(); pp.ref_code = ctx->d_ref_code.as<uint8_t>(); pp.reads_raw = ctx->d_reads.as<uint8_t>();
+  pp.qpairs = ctx->d_qpairs.as<uint32_t>(); pp.table = ctx->d_table.as<int16_t>(); pp.KP = ctx->KP;
+  pp.pairs = lc.d_pairs.as<PairDesc>(); pp.npairs = 1;
+  pp.blkmax = ctx->d_blkmax.as<uint32_t>(); pp.ckpt = ctx->d_ckpt.as<uint32_t>(); pp.bnd = ctx->d_bnd.as<uint32_t>();
+  pp.L = lc.geo.L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
+  pp.sc = device_scoring(ctx->sc, false);
+  dp.out = d_out.as<int32_t>(); dp.m = (int)m; dp.n = (int)n;
+  const size_t smem = profile ? (size_t)ctx->KP * lc.geo.R * 32 * 4 : 0;
+  cudaError_t e = launch_dump(lc.geo.R, sat, profile, smem, ctx->stream, dp);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, (m + 1) * (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  d_out.release();
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SWB_ERR_CUDA; }
+  return SWB_OK;
 }
 
 }  // extern "C"

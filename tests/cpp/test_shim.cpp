@@ -51,6 +51,16 @@ int main() {
     catch (const swb::Error& e) { threw = e.code == SWB_ERR_RANGE; }
     EXPECT(threw);    // the reference aborts on this assert (plocalaligner.cpp:52)
   }
+  {
+    // test/test_skewedmatrix.cpp:39-66: every cell of the two SMTs agrees (through getSimilarity_matrix())
+    const std::string a = "GGTTGACTA", b = "TGTTACG";
+    CUDASWAligner<CUDA_Similarity_Matrix_Skewed> s1(a, b);
+    CUDASWAligner<CUDA_Similarity_Matrix> s2(a, b);
+    s1.calculateScore(); s2.calculateScore();
+    for (size_t i = 0; i <= a.size(); ++i)
+      for (size_t j = 0; j <= b.size(); ++j) EXPECT(s1.getSimilarity_matrix()(i, j) == s2.getSimilarity_matrix()(i, j));
+    EXPECT(s1.getSimilarity_matrix()(7, 6) == 13.f);
+  }
   std::printf("SHIM OK\n");
   return 0;
 }

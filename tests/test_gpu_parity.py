@@ -211,3 +211,49 @@ def test_long_pair_c5_shape(engine, pkg):
         r = engine.align(reads, cons_stride=25_000)
         for i, x in enumerate(reads):
             _check(r, i, o.align(x, ref, mode=omode), tag=("c5", mode))
+
+
+def test_dense_matrix_accessor(engine, pkg):
+    """operator()(row, col) surface: every cell of H through the device path equals the oracle
+    (test/test_skewedmatrix.cpp:39-66 compares the two SMTs cell by cell; test_localaligner.cpp:31-42 golden H)."""
+    want = o.matrix("GGTTGACTA", "TGTTACGG", mode=o.MODE_SAT_U8)
+    for mode in (pkg.MODE_SAT_U8, pkg.MODE_EXACT):
+        engine.set_scoring_match(mode, 3, -3, 2)
+        engine.set_reference("TGTTACGG")
+        assert (engine.matrix("GGTTGACTA") == want).all()
+    rng = np.random.default_rng(17)
+    for (m, n) in ((9, 7), (7, 9), (130, 77), (64, 300), (700, 90), (1300, 200)):
+        x = "".join(rng.choice(list("ACGT"), size=m))
+        y = "".join(rng.choice(list("ACGT"), size=n))
+        for mode, omode, sc in ((pkg.MODE_SAT_U8, o.MODE_SAT_U8, (40, -7, 9)), (pkg.MODE_EXACT, o.MODE_EXACT, (3, -3, 2))):
+            engine.set_scoring_match(mode, *sc)
+            engine.set_reference(y)
+            got = engine.matrix(x)
+            exp = o.matrix(x, y, mode=omode, match=sc[0], mismatch=sc[1], gap=sc[2])
+            assert (got == exp).all(), (m, n, mode)
+    t = synth.blosum62_table()
+    q = synth.c4_queries(1, 120)[0]
+    prot = synth.c4_database(3)[0][:200]
+    engine.set_scoring_table(pkg.MODE_EXACT, t, 10)
+    engine.set_reference(q)
+    assert (engine.matrix(prot) == o.matrix(prot, q, mode=o.MODE_EXACT, table=t, gap=10)).all()
+
+
+def test_consensus_truncation_flag_and_errors(engine, pkg):
+    """A consensus longer than cons_stride is flagged (score / end cell stay exact); bad arguments return codes."""
+    rng = np.random.default_rng(4)
+    y = "".join(rng.choice(list("ACGT"), size=900))
+    x = y[100:400]
+    engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
+    engine.set_reference(y)
+    full = engine.align([x], cons_stride=700)
+    cut = engine.align([x], cons_stride=64)
+    assert full["flags"][0] == 0 and cut["flags"][0] & 1
+    assert int(cut["score"][0]) == int(full["score"][0]) == 900 and tuple(cut["end"][0]) == tuple(full["end"][0])
+    with pytest.raises(pkg.SwbError) as ei:
+        engine.align(["ACGT", ""])
+    assert ei.value.code == -2
+    with pytest.raises(pkg.SwbError) as ei:
+        engine.set_scoring_match(pkg.MODE_EXACT, 2.5, -3, 2)
+    assert ei.value.code == -4
+    engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
