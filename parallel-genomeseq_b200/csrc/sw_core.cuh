@@ -366,8 +366,14 @@ struct Wavefront {
     }
     return (bnd_in && j <= (int)pd.n) ? ((volatile const uint32_t*)bnd_in)[j] : p.sc.negG2;
   }
-  template <bool BND, class Hook>
-  __device__ __forceinline__ void one_step(const PairDesc& pd, int t, const uint32_t (&ycur)[C], uint32_t& bmax, Hook&& hook) {
+  // ---- software-pipelined stepping -------------------------------------------------------------------------
+  // Symbols are loaded two steps ahead; with the profile select the scores of step t+1 are fetched from shared
+  // memory (into ra / rb) while step t computes, so no step waits on an LDS or an LDG.
+  uint32_t py0[C], py1[C];
+  RegSelect<R, C> ra, rb;
+
+  template <bool BND, class Sel, class Hook>
+  __device__ __forceinline__ void step_sel(const PairDesc& pd, int t, const Sel& sel, uint32_t& bmax, Hook&& hook) {
     uint32_t upv[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -381,16 +387,7 @@ struct Wavefront {
         if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
       }
     }
-    auto h = [&](int k, int c, uint32_t e_new) { hook(k, col_of<C>(t, g, c), e_new); };
-    if (PROFILE) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) psel.set_column(c, ycur[c]);
-      step<R, C, SAT>(st, psel, p.sc, upv, bmax, h);
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) csel.set_column(c, ycur[c]);
-      step<R, C, SAT>(st, csel, p.sc, upv, bmax, h);
-    }
+    step<R, C, SAT>(st, sel, p.sc, upv, bmax, [&](int k, int c, uint32_t e_new) { hook(k, t, col_of<C>(t, g, c), e_new); });
     if (BND) {
       const int j = col_of<C>(t, g, 0);
       if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) {
@@ -399,125 +396,88 @@ struct Wavefront {
       }
     }
   }
+  // make the pipeline ready to execute step t
+  __device__ __forceinline__ void prime(const PairDesc& pd, int t) {
+    if (PROFILE) {
+      load_symbols_m<true>(pd, t, py0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) psel.set_column(c, py0[c]);
+      ra.fetch(psel);
+      load_symbols_m<true>(pd, t + 1, py0);               // py0 = symbols of step t+1
+    } else {
+      load_symbols_m<true>(pd, t, py0);                   // py0 = symbols of step t
+      load_symbols_m<true>(pd, t + 1, py1);               // py1 = symbols of step t+1
+    }
+  }
+  // steps t and t+1; hook(k, step, j, E_new)
+  template <bool MASKED, bool BND, class Hook>
+  __device__ __forceinline__ void two_steps(const PairDesc& pd, int t, uint32_t& bmax, Hook&& hook) {
+    if (PROFILE) {
+      load_symbols_m<MASKED>(pd, t + 2, py1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) psel.set_column(c, py0[c]);
+      rb.fetch(psel);                                     // scores of step t+1
+      step_sel<BND>(pd, t, ra, bmax, hook);
+      load_symbols_m<MASKED>(pd, t + 3, py0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) psel.set_column(c, py1[c]);
+      ra.fetch(psel);                                     // scores of step t+2
+      step_sel<BND>(pd, t + 1, rb, bmax, hook);
+    } else {
+      uint32_t y2[C];
+      load_symbols_m<MASKED>(pd, t + 2, y2);
+#pragma unroll
+      for (int c = 0; c < C; ++c) csel.set_column(c, py0[c]);
+      step_sel<BND>(pd, t, csel, bmax, hook);
+      load_symbols_m<MASKED>(pd, t + 3, py0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) csel.set_column(c, py1[c]);
+      step_sel<BND>(pd, t + 1, csel, bmax, hook);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { const uint32_t tmp = py0[c]; py0[c] = y2[c]; py1[c] = tmp; }
+    }
+  }
   template <bool BND>
   __device__ __forceinline__ void begin(const PairDesc& pd, int t0) {
     restore(pd, t0);
     if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
+    prime(pd, t0 + 1);
   }
   template <bool BND, class Hook>
   __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
     begin<BND>(pd, t0);
     uint32_t bmax = NEG_INF2;
-    uint32_t ynext[C];
-    load_symbols(pd, t0 + 1, ynext);
-    for (int s = 1; s <= nsteps; ++s) {
-      const int t = t0 + s;
-      uint32_t ycur[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
-      load_symbols(pd, t + 1, ynext);
-      const bool on = t <= t1;
-      one_step<BND>(pd, t, ycur, bmax, [&](int k, int j, uint32_t e_new) { if (on) hook(k, j, e_new); });
-    }
+    for (int s = 1; s <= nsteps; s += 2)
+      two_steps<true, BND>(pd, t0 + s, bmax, [&](int k, int t, int j, uint32_t e_new) { if (t <= t1) hook(k, j, e_new); });
   }
   // replay never writes boundary rows again (bnd_out is cleared), it only reads them
   template <class Hook>
   __device__ __forceinline__ void replay(const PairDesc& pd, bool multi, int t0, int t1, int nsteps, Hook&& hook) {
-    bnd_out = nullptr;
+    bnd_out = nullptr; wait_on = nullptr; publish_to = nullptr;
     if (C == 1 && multi) replay_impl<true>(pd, t0, t1, nsteps, hook);
     else replay_impl<false>(pd, t0, t1, nsteps, hook);
   }
 };
 
 // ======================================================================================================
-// Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp.
+// Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp (or one warp per strip).
+// Blocks whose columns (plus the two-step look-ahead) are inside [1, n] for every lane skip the range tests.
 // ======================================================================================================
 template <int R, int C, bool SAT, bool PROFILE, bool BND>
-__device__ __forceinline__ void score_strip(Wavefront<R, C, SAT, PROFILE>& wf, const PassParams& p, const PairDesc& pd, int steps, bool live) {
+__device__ __forceinline__ void score_pass(Wavefront<R, C, SAT, PROFILE>& wf, const PassParams& p, const PairDesc& pd,
+                                           int steps, int n_min, bool live) {
   const int L = wf.L, g = wf.g;
   uint32_t* blk = p.blkmax + pd.blk_off;
   uint32_t* ck = p.ckpt + pd.ck_off;
   wf.template begin<BND>(pd, 0);
   uint32_t bmax = NEG_INF2;
-  uint32_t ynext[C];
-  wf.load_symbols(pd, 1, ynext);
-  for (int t = 1; t <= steps; ++t) {
-    uint32_t ycur[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
-    wf.load_symbols(pd, t + 1, ynext);
-    wf.template one_step<BND>(pd, t, ycur, bmax, [](int, int, uint32_t) {});
-    if ((t & (p.B - 1)) == 0) {
-      const int b = (t >> p.logB) - 1;
-      const uint32_t gm = group_max_s16x2(bmax, L);
-      if (live && b < (int)pd.nblk) {
-        if (g == 0) blk[wf.blk_index(pd, b)] = gm;
-        save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
-      }
-      bmax = NEG_INF2;
-    }
-  }
-}
-
-// Single-strip score pass, software-pipelined: symbols are loaded two steps ahead and (profile select) the
-// scores of step t+1 are fetched from shared memory while step t computes.  Blocks whose columns (plus the
-// two-step look-ahead) are inside [1, n] for every lane of the warp skip the range tests.
-template <int R, int C, bool SAT, bool PROFILE>
-__device__ __forceinline__ void score_single(Wavefront<R, C, SAT, PROFILE>& wf, const PassParams& p, const PairDesc& pd,
-                                             int steps, int n_min, bool live) {
-  const int L = wf.L, g = wf.g;
-  uint32_t* blk = p.blkmax + pd.blk_off;
-  uint32_t* ck = p.ckpt + pd.ck_off;
-  wf.restore(pd, 0);
-  uint32_t bmax = NEG_INF2;
-  uint32_t y0[C], y1[C];               // symbols of steps t and t+1 (compare) / t+1 and t+2 (profile)
-  RegSelect<R, C> ra, rb;              // profile select: scores of the current / next step
-  if (PROFILE) {
-    wf.template load_symbols_m<true>(pd, 1, y0);
-#pragma unroll
-    for (int c = 0; c < C; ++c) wf.psel.set_column(c, y0[c]);
-    ra.fetch(wf.psel);
-    wf.template load_symbols_m<true>(pd, 2, y0);     // y0 = step t+1
-  } else {
-    wf.template load_symbols_m<true>(pd, 1, y0);     // y0 = step t
-    wf.template load_symbols_m<true>(pd, 2, y1);     // y1 = step t+1
-  }
+  auto nohook = [](int, int, int, uint32_t) {};
   const int nb = steps >> p.logB;
   for (int b = 0; b < nb; ++b) {
     const int t0 = b << p.logB;
     const bool interior = (t0 + 1 >= L) && ((t0 + p.B + 2) * C <= n_min);
-    auto run = [&](auto masked_tag) {
-      constexpr bool MASKED = decltype(masked_tag)::value;
-      for (int t = t0 + 1; t <= t0 + p.B; t += 2) {
-        if (PROFILE) {
-          // step t (scores in ra); fetch scores of t+1 into rb; load symbols of t+2
-          wf.template load_symbols_m<MASKED>(pd, t + 2, y1);
-#pragma unroll
-          for (int c = 0; c < C; ++c) wf.psel.set_column(c, y0[c]);
-          rb.fetch(wf.psel);
-          wf.step_with(ra, bmax);
-          // step t+1 (scores in rb); fetch scores of t+2 into ra; load symbols of t+3
-          wf.template load_symbols_m<MASKED>(pd, t + 3, y0);
-#pragma unroll
-          for (int c = 0; c < C; ++c) wf.psel.set_column(c, y1[c]);
-          ra.fetch(wf.psel);
-          wf.step_with(rb, bmax);
-        } else {
-          uint32_t y2[C];
-          wf.template load_symbols_m<MASKED>(pd, t + 2, y2);
-#pragma unroll
-          for (int c = 0; c < C; ++c) wf.csel.set_column(c, y0[c]);
-          wf.step_with(wf.csel, bmax);
-          wf.template load_symbols_m<MASKED>(pd, t + 3, y0);
-#pragma unroll
-          for (int c = 0; c < C; ++c) wf.csel.set_column(c, y1[c]);
-          wf.step_with(wf.csel, bmax);
-#pragma unroll
-          for (int c = 0; c < C; ++c) { const uint32_t tmp = y0[c]; y0[c] = y2[c]; y1[c] = tmp; }
-        }
-      }
-    };
-    if (interior) run(std::false_type{}); else run(std::true_type{});
+    if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps<false, BND>(pd, t, bmax, nohook); }
+    else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps<true, BND>(pd, t, bmax, nohook); }
     const uint32_t gm = group_max_s16x2(bmax, L);
     if (live && b < (int)pd.nblk) {
       if (g == 0) blk[wf.blk_index(pd, b)] = gm;
@@ -548,7 +508,7 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
     wf.prepare(pd, (int)u.y, prof_warp);
     wf.wait_on = u.y > 0 ? p.progress + (gwarp - 1) : nullptr;
     wf.publish_to = (u.y + 1 < pd.nstrips) ? p.progress + gwarp : nullptr;
-    score_strip<R, C, SAT, PROFILE, true>(wf, p, pd, (int)pd.nblk << p.logB, true);
+    score_pass<R, C, SAT, PROFILE, true>(wf, p, pd, (int)pd.nblk << p.logB, (int)pd.n, true);
     return;
   }
   int pair = gwarp * groups_per_warp + (lane >> p.logL);
@@ -562,19 +522,19 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   // run whole blocks so that every lane flushes together; lanes past their range see sentinel columns
   const int steps = warp_max_i32((int)pd.nblk << p.logB);
   const int nstrips = warp_max_i32((int)pd.nstrips);    // > 1 only with L == 32 (one pair per warp)
+  int n_min = (int)pd.n;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_min = min(n_min, __shfl_xor_sync(0xffffffffu, n_min, o));
   if (C == 1 && nstrips > 1) {
     for (int s = 0; s < nstrips; ++s) {
       wf.prepare(pd, s, prof_warp);
-      score_strip<R, C, SAT, PROFILE, true>(wf, p, pd, steps, live);
+      score_pass<R, C, SAT, PROFILE, true>(wf, p, pd, steps, n_min, live);
       __syncwarp();                       // boundary row of strip s is complete before strip s+1 reads it
       __threadfence_block();
     }
   } else {
-    int n_min = (int)pd.n;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_min = min(n_min, __shfl_xor_sync(0xffffffffu, n_min, o));
     wf.prepare(pd, 0, prof_warp);
-    score_single<R, C, SAT, PROFILE>(wf, p, pd, steps, n_min, live);
+    score_pass<R, C, SAT, PROFILE, false>(wf, p, pd, steps, n_min, live);
   }
 }
 
@@ -639,7 +599,10 @@ __device__ __forceinline__ int group_max_i32(int v, int L) {
 }
 
 template <int R, int C, bool SAT, bool PROFILE>
-__global__ void __launch_bounds__(128) trace_kernel(const TraceParams tp) {
+#ifndef SWB_TRACE_MINBLOCKS
+#define SWB_TRACE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const TraceParams tp) {
   extern __shared__ uint32_t smem_prof[];
   const PassParams& p = tp.pp;
   const int lane = threadIdx.x & 31;

@@ -287,10 +287,18 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= want) r_strip = kRSet[i];
     }
   }
+  // ragged batches (a protein database): one strip-geometry class for every length instead of a launch class
+  // per (L, R) combination — a single score launch and a single trace launch, longest sequences first
+  const bool ragged = count_by_m.size() > 8;
+  if (ragged && !getenv("SWB_STRIP_R")) {
+    const int cap = 4;      // thin strips: pass 2 replays O(rows-in-strip) columns per strip (measured best on B200)
+    r_strip = kRSet[0];
+    for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= cap && kRSet[i] <= r_hard) r_strip = kRSet[i];
+  }
   for (auto& kv : count_by_m) {
     Geometry g;
     const int r_cap = profile ? std::max(r_pref, kRSet[0]) : 32;
-    if (ctx->force_l32 || (int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
+    if (ctx->force_l32 || ragged || (int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
       // longer than one warp holds at the preferred rows-per-lane: row strips of 32 x R rows, processed top
       // to bottom (the strip count is per pair, so one launch class serves every length)
       g.L = 32; g.logL = 5; g.R = r_strip; g.nstrips = 0;     // 0 = "per pair"
