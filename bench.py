@@ -52,6 +52,20 @@ def load_peaks():
     return p_int, src, hbm, hsrc
 
 
+def load_traffic(n_reads):
+    """dram__bytes_read + dram__bytes_write of one score-kernel launch from the committed ncu capture, when it was
+    taken at this batch size (profiles/ncu_traffic_r*.json); None otherwise."""
+    prof = os.path.join(ROOT, "profiles")
+    if os.path.isdir(prof):
+        for fn in sorted(os.listdir(prof), reverse=True):
+            if fn.startswith("ncu_traffic_r") and fn.endswith(".json"):
+                with open(os.path.join(prof, fn)) as f:
+                    k = json.load(f)["score_kernel"]
+                if k["reads_per_gpu"] == n_reads:
+                    return k["dram_bytes_read"] + k["dram_bytes_write"]
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -155,7 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=28416, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=37888, help="reads per GPU per step")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU-baseline sample (default 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -278,7 +292,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": p_int, "unit": "Tops/s (int lane-ops)", "frac": achieved / p_int,
-                         "traffic": None, "ops_per_cell": ops, "kernel": "score_kernel (pass 1)", "kernel_gcups": k_gcups, "kernel_ms": pass1_us / 1e3,
+                         "traffic": load_traffic(n_reads), "traffic_unit": "bytes per score_kernel launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "ops_per_cell": ops, "kernel": "score_kernel (pass 1)", "kernel_gcups": k_gcups, "kernel_ms": pass1_us / 1e3,
                          "kernel_share_of_step": pass1_us / step_us, "peak_source": p_src,
                          "executed_cell_fraction": cells_step / max(1, st["cells_executed"]),
                          "hbm": {"achieved_gbs": hbm_bytes / (pass1_us * 1e-6) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src}},

@@ -10,7 +10,7 @@
 // Design (B200-first, not a port of the AVX2 skewed-matrix code):
 //   * The full H matrix is never materialised.  A "pair" packs TWO alignments against the same
 //     y-range into the two signed 16-bit halves of every 32-bit register (s16x2); one DP cell pair
-//     costs four DPX instructions (VIADDMNMX.S16x2[.RELU], VIMNMX.S16x2) — see step() below.
+//     costs three DPX instructions plus half a VIMNMX3 — see step() below.
 //   * L lanes (a power of two, a sub-warp "group") stripe the rows of one pair, R rows per lane in
 //     registers.  Lane g works on column j = t - g at step t (a skewed wavefront); the row carry
 //     between neighbouring lanes is one __shfl_up_sync per step.
@@ -18,11 +18,15 @@
 //         d    = max(E_nw + (s+G), E_w, 0)            one VIADDMNMX.S16x2.RELU   (= max(NW+s, W-G, 0))
 //         dG   = min(d - G, 255 - G)                  one VIADDMNMX (min form)   (u8 saturation, SAT_U8)
 //         E    = max(E_n - G, dG)                     one VIADDMNMX              (= H - G)
-//         bmax = max(bmax, E)                         one VIMNMX.S16x2
-//   * Every B steps each lane flushes its block maximum and checkpoints its register state
-//     (R+1 words).  Pass 2 (locate + traceback) restarts the same wavefront from a checkpoint, so the
-//     arg-max tie-break of the reference and its value-greedy traceback are reproduced exactly while
-//     only O(B * m) cells are ever recomputed.
+//         bmax = max(bmax, E, E')                     one VIMNMX3.S16x2 per two cells
+//   * Symbol scores come from a per-warp query profile in shared memory (one LDS per cell pair, fetched
+//     one step ahead into registers) or, for big alphabets with match/mismatch scoring, from HSET2 + LOP3.
+//   * Every B steps each group stores its block maximum and every lane checkpoints its register state.
+//     Pass 2 (locate + traceback) restarts the same wavefront from a checkpoint, so the arg-max
+//     tie-break of the reference and its value-greedy traceback are reproduced exactly while only
+//     O(B * m) cells are ever recomputed.
+//   * Sequences longer than one warp holds are cut into row strips that hand their last row over
+//     through HBM; with few long pairs the strips of a pair run concurrently, one warp each.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -171,9 +175,6 @@ __device__ __forceinline__ void step(LaneState<R, C>& st, const Select& sel, con
   st.up_prev = upv[C - 1];
 }
 
-struct NoHook {
-  __device__ __forceinline__ void operator()(int, int, uint32_t) const {}
-};
 
 // y symbol for column j (1-based) of a pair's range, or the sentinel outside [1, n].  MASKED = false skips the
 // range test (interior blocks of the score pass, where every lane's column is known to be inside the range).
@@ -329,25 +330,10 @@ struct Wavefront {
     if (t0 == 0) init_state<R, C>(st, p.sc);
     else load_state<R, C, SAT>(st, p.sc, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
   }
-  __device__ __forceinline__ void load_symbols(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
-#pragma unroll
-    for (int c = 0; c < C; ++c) y[c] = load_y<PROFILE>(p, pd, col_of<C>(t, g, c));
-  }
   template <bool MASKED>
   __device__ __forceinline__ void load_symbols_m(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
 #pragma unroll
     for (int c = 0; c < C; ++c) y[c] = load_y<PROFILE, MASKED>(p, pd, col_of<C>(t, g, c));
-  }
-  // one step with the scores supplied by `sel` (single-strip fast path of the score pass: no hook)
-  template <class Sel>
-  __device__ __forceinline__ void step_with(const Sel& sel, uint32_t& bmax) {
-    uint32_t upv[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      upv[c] = __shfl_up_sync(0xffffffffu, st.bot[c], 1, L);
-      if (g == 0) upv[c] = p.sc.negG2;
-    }
-    step<R, C, SAT>(st, sel, p.sc, upv, bmax, NoHook());
   }
   // 32 boundary columns starting at column 32*k + 1, one per lane
   __device__ __forceinline__ uint32_t load_chunk(const PairDesc& pd, int k) const {

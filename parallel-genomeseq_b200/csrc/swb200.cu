@@ -101,8 +101,6 @@ struct swb_ctx {
   int B = 64, logB = 6;
   bool force_l32 = false;           // swb_matrix: always the 32-lane geometry (one pair per warp)
   int C = 1;                        // columns per wavefront step (2 = more ILP per warp; measured slower on B200, kept selectable)
-  std::vector<uint64_t> offsets;
-  std::vector<char> seq_host;       // kept for the custom-scoring re-alignment of the chunked path
   std::vector<LaunchClass> classes;
   DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
@@ -673,10 +671,7 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
   if (!hs.match_shaped && ctx->KP > 200) return fail(ctx, SWB_ERR_UNSUPPORTED, "tabulated scoring needs a reference alphabet of at most 199 symbols");
 
   ctx->n_seqs = n_seqs; ctx->npiece = npiece; ctx->ratio = ratio; ctx->flags = flags; ctx->cons_stride = cons_stride;
-  ctx->offsets.assign(offsets, offsets + n_seqs + 1);
   const bool chunked = npiece >= 1;
-  const bool realign = chunked && !hs.is_default();
-  if (realign) ctx->seq_host.assign(seqs + offsets[0], seqs + offsets[n_seqs]); else ctx->seq_host.clear();
 
   // tasks
   const int pieces = chunked ? npiece : 1;

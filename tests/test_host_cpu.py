@@ -134,3 +134,29 @@ def test_sharding_and_gather_world_size_2_gloo(tmp_path):
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, out
         assert f"rank {r} ok" in out
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference times the reference's own CPU implementation (oracle/_ref, else the oracle port)
+    and prints one JSON line with the contract keys — no GPU needed."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-reads", "2"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().split("\n")[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GCUPS" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_bench_peaks_and_metric_contract():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    p_int, src, hbm, hsrc = b.load_peaks()
+    assert 10.0 < p_int < 40.0 and hbm > 1000
+    import json
+    with open(os.path.join(ROOT, "BASELINE.json")) as f:
+        assert b.METRIC == json.load(f)["metric"]
+    assert b.OPS_PER_CELL["SAT_U8"] == 9 and b.OPS_PER_CELL["EXACT"] == 8

@@ -22,17 +22,17 @@ def main(path):
         if k in hdr:
             i = hdr.index(k)
             print(f"{k:72s} {vals[i]} {units[i]}")
-    print("\nwarp stall reasons (> 1 % of issue-stalled warp samples, per active warp):")
+    print("\nwarp stall reasons (average warps stalled per issue-active cycle):")
     st = []
     for i, h in enumerate(hdr):
-        if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
             try:
                 st.append((float(vals[i]), h))
             except ValueError:
                 pass
     for v, h in sorted(st, reverse=True):
-        if v > 1.0:
-            print(f"  {h.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', ''):40s} {v:6.1f} %")
+        if v > 0.05:
+            print(f"  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):40s} {v:6.2f}")
 
 
 if __name__ == "__main__":
