@@ -429,14 +429,36 @@ struct Wavefront {
     if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
     prime(pd, t0 + 1);
   }
+  // Pass-2 replay: a plain one-step loop (scores straight from the select, symbols one step ahead).  Pass 2
+  // is short and has several replay sites per kernel; the compact body keeps them inside the instruction
+  // cache, which matters more there than the software pipelining of the score pass.
   template <bool BND, class Hook>
   __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
-    begin<BND>(pd, t0);
+    restore(pd, t0);
+    if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
     uint32_t bmax = NEG_INF2;
-    for (int s = 1; s <= nsteps; s += 2)
-      two_steps<true, BND>(pd, t0 + s, bmax, [&](int k, int t, int j, uint32_t e_new) { if (t <= t1) hook(k, j, e_new); });
+    uint32_t ynext[C];
+    load_symbols_m<true>(pd, t0 + 1, ynext);
+    for (int s = 1; s <= nsteps; ++s) {
+      const int t = t0 + s;
+      uint32_t ycur[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
+      load_symbols_m<true>(pd, t + 1, ynext);
+      const bool on = t <= t1;
+      auto h = [&](int k, int, int j, uint32_t e_new) { if (on) hook(k, j, e_new); };
+      if (PROFILE) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) psel.set_column(c, ycur[c]);
+        step_sel<BND>(pd, t, psel, bmax, h);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) csel.set_column(c, ycur[c]);
+        step_sel<BND>(pd, t, csel, bmax, h);
+      }
+    }
   }
-  // replay never writes boundary rows again (bnd_out is cleared), it only reads them
+  // replay never writes boundary rows or progress counters again, it only reads boundary rows
   template <class Hook>
   __device__ __forceinline__ void replay(const PairDesc& pd, bool multi, int t0, int t1, int nsteps, Hook&& hook) {
     bnd_out = nullptr; wait_on = nullptr; publish_to = nullptr;
