@@ -437,14 +437,15 @@ struct Wavefront {
     restore(pd, t0);
     if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
     uint32_t bmax = NEG_INF2;
-    uint32_t ynext[C];
+    uint32_t ynext[C], ynext2[C];                          // symbols of the next two steps (loads stay two steps ahead)
     load_symbols_m<true>(pd, t0 + 1, ynext);
+    load_symbols_m<true>(pd, t0 + 2, ynext2);
     for (int s = 1; s <= nsteps; ++s) {
       const int t = t0 + s;
       uint32_t ycur[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) ycur[c] = ynext[c];
-      load_symbols_m<true>(pd, t + 1, ynext);
+      for (int c = 0; c < C; ++c) { ycur[c] = ynext[c]; ynext[c] = ynext2[c]; }
+      load_symbols_m<true>(pd, t + 2, ynext2);
       const bool on = t <= t1;
       auto h = [&](int k, int, int j, uint32_t e_new) { if (on) hook(k, j, e_new); };
       if (PROFILE) {
@@ -564,8 +565,9 @@ struct TraceParams {
   const uint32_t* task_list;
   int ntasks;
   int mode;                   // MODE_SAT_U8: skewed raw-order tie-break; MODE_EXACT: column-major
-  uint32_t* scratch;          // per group: Wc columns x rstride rows of packed E words
-  int Wc, rstride;            // ring width (power of two), rows per column (L*R + 1)
+  int max_pos;                // largest positive substitution score: a cell of score V needs row >= ceil(V / max_pos)
+  uint32_t* scratch;          // per group: ring of the last Wc steps, word (((t & (Wc-1)) * C + c) * R + k) * L + g
+  int Wc, rstride;            // ring depth in steps (power of two); rstride = C * R * L words per step
   int32_t* out_score;
   uint32_t* out_pos;
   uint32_t* out_end;          // 2 per task: index_x, index_y of the arg-max
@@ -575,6 +577,8 @@ struct TraceParams {
   uint32_t cons_cap;          // bytes per task in out_cx / out_cy
   uint32_t* out_flags;        // bit0: consensus overflowed cons_cap
   int want_consensus;
+  int dbg_flags;                  // diagnostics: bit0 skip ring stores, bit1 skip the walk (results are then wrong)
+  unsigned long long* counters;   // diagnostics (SWB_DEBUG): [0] scan replays, [1] sessions, [2] scan lockstep rounds, [3] session rounds, [4] session steps (warp max)
 };
 
 __device__ __forceinline__ int half_of(uint32_t v, uint32_t half) { return (int)(int16_t)(half ? (v >> 16) : (v & 0xFFFFu)); }
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int ggroup = gwarp * groups_per_warp + grp_in_warp;
-  uint32_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;
+  uint32_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;   // ring of recomputed steps, lane-contiguous words
   const int wmask = tp.Wc - 1;
   const int G = p.sc.G;
   const int S = L * R;                 // rows per strip
@@ -646,8 +650,10 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
     const uint32_t half = td.half;
     const uint8_t* xraw = p.reads_raw + (td.half ? pd.xB : pd.xA);
     const uint8_t* yraw = p.ref_raw + pd.y_off;
+    long long tk0 = clock64();
     int cur_strip = 0;
     wf.prepare(pd, 0, prof_warp);
+    if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 8, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
 
     // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------------
     const uint32_t* blk = p.blkmax + pd.blk_off;
@@ -655,6 +661,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
     for (int w = g; w < nunits; w += L) vmax = max(vmax, half_of(blk[w], half));
     vmax = group_max_i32(vmax, L);
     const int score = vmax + G;
+    if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 9, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
     if (active && (m == 0 || score <= 0)) {
       // all-zero matrix: the reference reads H(-1,-1) (undefined); we return score 0, pos 0, "".
       if (g == 0) {
@@ -670,6 +677,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
     // key already exceeds the current winner are skipped; units that may hold wrapped (lower-triangle) cells
     // sort first in the skewed order and are visited first (phase 0), the others in phase 1.
     const int ncols_raw = max(n + 1, m + 1);
+    const int row_min = (score + tp.max_pos - 1) / max(tp.max_pos, 1);   // a cell worth `score` cannot sit above this row
     uint64_t best = ~0ull;
     int cursor = active ? 0 : 2 * nunits;            // [0, nunits): phase 0, [nunits, 2*nunits): phase 1
     const uint32_t vmax2 = (uint32_t)(uint16_t)(int16_t)vmax * 0x00010001u;
@@ -689,7 +697,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
           if (half_of(blk[u], half) == vmax) {
             const int t0 = ub << p.logB;
             const int jmin = max(1, C * (t0 - (L - 1)) + 1), jmax = min(n, C * (t0 + p.B));
-            const int imin = us * S + 1, imax = min(m, (us + 1) * S);
+            const int imin = max(us * S + 1, row_min), imax = min(m, (us + 1) * S);
             if (jmin <= jmax && imin <= imax) {
               const bool wraps = tp.mode == MODE_SAT_U8 && (jmax + imax >= ncols_raw);
               uint64_t lb;
@@ -706,8 +714,10 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
           if (cm) { myu = usel; cursor += q + 1; } else { cursor += L; }
         }
       }
+      if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 10, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
       if (!__any_sync(0xffffffffu, myu >= 0)) break;
       const bool has = myu >= 0;
+      if (tp.counters) { if (has && g == 0) atomicAdd(tp.counters + 0, 1ull); if (lane == 0) atomicAdd(tp.counters + 2, 1ull); }
       const int us = has ? myu / nblk : cur_strip;
       const int t0 = has ? ((myu - us * nblk) << p.logB) : 0;
       if (multi && us != cur_strip) { cur_strip = us; wf.prepare(pd, us, prof_warp); }
@@ -724,6 +734,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       });
       mine = group_min_u64(mine, L);
       best = mine < best ? mine : best;
+      if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 11, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
     }
     int ie = 1, je = 1;
     if (active) {
@@ -762,44 +773,86 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       int c_lo = iy - 2 - (il + 8);      // restart at a checkpoint left of the columns the remaining rows can reach
       if (c_lo < 0) c_lo = 0;
       const int t_lo = done ? 0 : (((c_lo / C) >> p.logB) << p.logB);
-      const int valid_lo = max(C * t_lo, C * t_hi - tp.Wc + 1);     // oldest column every lane still holds
+      const int valid_lo = max(C * t_lo, C * (t_hi - tp.Wc) + 1);   // oldest column every lane still holds
       if (multi && !done && ss != cur_strip) { cur_strip = ss; wf.prepare(pd, ss, prof_warp); }
-      const int srow0 = g * R + 1;                       // first strip-local row of this lane
+      // ring slot of (step t, column-in-step c, row-in-lane k, lane g): all 32 lanes of a store are contiguous
+      auto slot = [&](int t, int c, int k, int gg) -> size_t { return ((size_t)((t & wmask) * C + c) * R + k) * L + gg; };
       if (!done && t_lo > 0) {
-        // the checkpoint itself is column C * (t_lo - g) of this lane's rows
+        // the checkpoint itself is the last column of step t_lo for every lane
         const uint32_t* ck = p.ckpt + pd.ck_off + wf.ck_index(pd, (t_lo >> p.logB) - 1);
-        const int jc = C * (t_lo - g);
-        if (jc >= 0) {
 #pragma unroll
-          for (int k = 0; k < R; ++k) scr[(size_t)(jc & wmask) * tp.rstride + srow0 + k] = ck_reg<R, C, SAT>(p.sc, ck, L, g, k);
-        }
+        for (int k = 0; k < R; ++k) scr[slot(t_lo, C - 1, k, g)] = ck_reg<R, C, SAT>(p.sc, ck, L, g, k);
       }
       const int nsteps = warp_max_i32(t_hi - t_lo);
+      if (tp.counters) { if (!done && g == 0) atomicAdd(tp.counters + 1, 1ull); if (lane == 0) { atomicAdd(tp.counters + 3, 1ull); atomicAdd(tp.counters + 4, (unsigned long long)nsteps); } }
       wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
-        if (j >= 0) scr[(size_t)(j & wmask) * tp.rstride + srow0 + k] = e_new;
+        // column j of lane g belongs to step g + ceil(j / C); virtual columns j <= 0 hold H = 0 and are never read
+        if (j >= 1 && !(tp.dbg_flags & 1)) scr[slot(step_of<C>(j, g), (j - 1) % C, k, g)] = e_new;
       });
       __syncwarp();
+      if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 12, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
       if (g == 0 && !done) {
-        // row 0 and column 0 of H are zero and never stored; stored words are packed E = H - G
+        // row 0 and column 0 of H are zero and never stored; stored words are packed E = H - G.
+        // cell_ptr: address of the packed word of H(i, j) — the ring, the boundary row of the strip above, or
+        // null for the zero border.  Loads are issued together (ld.global.cg), then decoded.
         const int row_lo = ss * S;                       // last row of the strip above (0 for strip 0)
         const uint32_t* above = ss > 0 ? p.bnd + pd.bnd_off + (size_t)(ss - 1) * (n + 1) : nullptr;
-        auto Hat = [&](int i, int j) -> int {
-          if (i <= 0 || j <= 0) return 0;
-          if (i == row_lo) return half_of(((volatile const uint32_t*)above)[j], half) + G;
-          return half_of(((volatile uint32_t*)scr)[(size_t)(j & wmask) * tp.rstride + (i - row_lo)], half) + G;
+        auto cell_ptr = [&](int i, int j) -> const uint32_t* {
+          if (i <= 0 || j <= 0) return nullptr;
+          if (i == row_lo) return above + j;
+          const int il2 = i - row_lo - 1;
+          const int gg = il2 / R;
+          return scr + slot(step_of<C>(j, gg), (j - 1) % C, il2 - gg * R, gg);
         };
-        while (true) {
+        // The walk is a chain of dependent loads; most moves are diagonal, so the three neighbours of the next
+        // SPEC cells along the diagonal are loaded together and consumed while the walk stays on the diagonal.
+        constexpr int SPEC = 4;
+        int v1[SPEC], v2[SPEC], v3[SPEC];
+        uint8_t xb[SPEC], yb[SPEC];                          // x[ix-d-1], y[iy-d-1]: the characters the consensus emits
+        int have = 0, at = 0;                                // v*[at] belongs to the current cell when at < have
+        if (tp.dbg_flags & 2) { done = true; }
+        while (!(tp.dbg_flags & 2)) {
           if (iy - 1 < valid_lo && iy - 1 > 0) break;        // ring exhausted: recompute further left
           if (ix <= row_lo) break;                           // walked into the strip above
-          const int n1 = Hat(ix - 1, iy - 1), n2 = Hat(ix, iy - 1), n3 = Hat(ix - 1, iy);
+          if (at >= have) {
+            // cells (ix-d, iy-d), d = 0..SPEC-1, as far as they stay inside the strip and the valid ring
+            const uint32_t* q1[SPEC]; const uint32_t* q2[SPEC]; const uint32_t* q3[SPEC];
+            bool okd[SPEC];
+#pragma unroll
+            for (int d = 0; d < SPEC; ++d) {
+              const int cx_ = ix - d, cy_ = iy - d;
+              okd[d] = d == 0 || (cx_ > row_lo && (cy_ - 1 >= valid_lo || cy_ - 1 <= 0) && cy_ >= 1);
+              q1[d] = okd[d] ? cell_ptr(cx_ - 1, cy_ - 1) : nullptr;
+              q2[d] = okd[d] ? cell_ptr(cx_, cy_ - 1) : nullptr;
+              q3[d] = okd[d] ? cell_ptr(cx_ - 1, cy_) : nullptr;
+            }
+            uint32_t w1[SPEC], w2[SPEC], w3[SPEC];
+#pragma unroll
+            for (int d = 0; d < SPEC; ++d) {                 // all loads first ...
+              w1[d] = q1[d] ? __ldcg(q1[d]) : p.sc.negG2; w2[d] = q2[d] ? __ldcg(q2[d]) : p.sc.negG2; w3[d] = q3[d] ? __ldcg(q3[d]) : p.sc.negG2;
+              const bool in = okd[d] && ix - d >= 1 && iy - d >= 1;
+              xb[d] = (in && tp.want_consensus) ? xraw[ix - d - 1] : (uint8_t)0;
+              yb[d] = (in && tp.want_consensus) ? yraw[iy - d - 1] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int d = 0; d < SPEC; ++d) {                 // ... then decode (E = -G encodes H = 0)
+              v1[d] = okd[d] ? half_of(w1[d], half) + G : -1; v2[d] = okd[d] ? half_of(w2[d], half) + G : -1; v3[d] = okd[d] ? half_of(w3[d], half) + G : -1;
+            }
+            have = SPEC; at = 0;
+          }
+          int n1 = 0, n2 = 0, n3 = 0;
+          uint8_t xc = 0, yc = 0;
+#pragma unroll
+          for (int d = 0; d < SPEC; ++d) if (d == at) { n1 = v1[d]; n2 = v2[d]; n3 = v3[d]; xc = xb[d]; yc = yb[d]; }
+          if (n1 < 0) { have = 0; continue; }                // speculation ran out of the safe region: reload here
           if (len >= tp.cons_cap) { flags |= 1u; done = true; break; }
           if (n1 == 0 || n2 == 0 || n3 == 0) {
-            if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = yraw[iy - 1]; }
+            if (tp.want_consensus) { cx[len] = xc; cy[len] = yc; }
             ++len; pos = (uint32_t)iy; done = true; break;
           }
-          if (n1 >= n2 && n1 >= n3) { if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = yraw[iy - 1]; } --ix; --iy; }
-          else if (n2 >= n1 && n2 >= n3) { if (tp.want_consensus) { cx[len] = '-'; cy[len] = yraw[iy - 1]; } --iy; }
-          else { if (tp.want_consensus) { cx[len] = xraw[ix - 1]; cy[len] = '-'; } --ix; }
+          if (n1 >= n2 && n1 >= n3) { if (tp.want_consensus) { cx[len] = xc; cy[len] = yc; } --ix; --iy; ++at; }
+          else if (n2 >= n1 && n2 >= n3) { if (tp.want_consensus) { cx[len] = '-'; cy[len] = yc; } --iy; have = 0; }
+          else { if (tp.want_consensus) { cx[len] = xc; cy[len] = '-'; } --ix; have = 0; }
           ++len;
         }
         if (done) {
@@ -809,6 +862,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
         }
       }
       __syncwarp();
+      if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 13, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
       // broadcast the walker's state to its group
       ix = __shfl_sync(0xffffffffu, ix, (int)gshift); iy = __shfl_sync(0xffffffffu, iy, (int)gshift);
       done = __shfl_sync(0xffffffffu, (int)done, (int)gshift) != 0;

@@ -147,7 +147,9 @@ int saturate_u8(float a) { if (a < 0) return 0; if (a > 255) return 255; return 
 bool choose_geometry(int m, size_t npairs, int r_cap, Geometry* out) {
   struct Cand { int L, R; double eff; double warps; };
   std::vector<Cand> c;
-  for (int L = 32; L >= 1; L >>= 1) {
+  int l_max = 32, l_min = 1;
+  if (const char* e = getenv("SWB_FORCE_L")) { l_max = l_min = std::max(1, std::min(32, atoi(e))); }
+  for (int L = l_max; L >= l_min; L >>= 1) {
     const int need = (m + L - 1) / L;
     int R = 0;
     for (int i = 0; i < kNumR; ++i) if (kRSet[i] >= need && kRSet[i] <= r_cap) { R = kRSet[i]; break; }
@@ -498,8 +500,9 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.task_list = task_list;
     tp.ntasks = ntrace;
     tp.mode = hs.mode;
+    tp.max_pos = force_default ? 3 : std::max(1, hs.max_pos);
     int wc = 64; while (wc < L * R + ctx->C * L + 24) wc <<= 1;
-    tp.Wc = wc; tp.rstride = L * R + 1;
+    tp.Wc = wc; tp.rstride = ctx->C * R * L;       // ring of the last Wc steps, C*R*L words per step
     const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(uint32_t);
     size_t max_groups = (size_t)148 * 16 * groups_per_warp;
     max_groups = std::min(max_groups, std::max<size_t>(groups_per_warp, ((size_t)2 << 30) / per_group));
@@ -519,11 +522,22 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.cons_cap = (uint32_t)ctx->cons_stride;
     tp.want_consensus = (ctx->flags & SWB_FLAG_CONSENSUS) ? 1 : 0;
     if (!tp.want_consensus) tp.cons_cap = 0x7FFFFFFFu;
+    DevBuf d_cnt;
+    tp.counters = nullptr;
+    tp.dbg_flags = getenv("SWB_DEBUG_FLAGS") ? atoi(getenv("SWB_DEBUG_FLAGS")) : 0;
+    if (dbg.on) { CUDA_TRY(d_cnt.ensure(128)); CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 128, ctx->stream)); tp.counters = d_cnt.as<unsigned long long>(); }
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
     CUDA_TRY(launch_trace(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
     CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->stats.kernel_launches++;
     dbg.mark("trace", L, R, (size_t)ntrace);
+    if (dbg.on) {
+      unsigned long long c[16] = {0};
+      cudaMemcpy(c, d_cnt.p, sizeof c, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[swb200]   scan replays %llu, sessions %llu, scan rounds (warps) %llu, session rounds (warps) %llu, session steps %llu\n", c[0], c[1], c[2], c[3], c[4]);
+      fprintf(stderr, "[swb200]   warp-cycles (M): prepare %.1f vmax %.1f search %.1f scan %.1f session %.1f walk %.1f\n", c[8] / 1e6, c[9] / 1e6, c[10] / 1e6, c[11] / 1e6, c[12] / 1e6, c[13] / 1e6);
+      d_cnt.release();
+    }
     ctx->stats.cells_pass2 += (uint64_t)ntrace * (uint64_t)(3 * ctx->B * ctx->C + lc.max_m + 16) * L * R * 2ull;
     ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
   }
