@@ -257,3 +257,65 @@ def test_consensus_truncation_flag_and_errors(engine, pkg):
         engine.set_scoring_match(pkg.MODE_EXACT, 2.5, -3, 2)
     assert ei.value.code == -4
     engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
+
+
+def test_edge_cases_against_oracle(engine, pkg):
+    """Ragged and degenerate inputs: single read, odd batch (an unpaired last task), 1- and 2-symbol sequences,
+    bytes outside ACGT ('N', lower case: scored by raw byte equality, similaritymatrix.cpp:415), duplicates,
+    a read equal to the whole reference window, a reference shorter than every read."""
+    rng = np.random.default_rng(31)
+    y = "".join(rng.choice(list("ACGTN"), size=400, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+    xs = ["A", "AC", y[10:11], y[5:130], y[5:130], y[100:240].lower(), y[100:240], "N" * 30 + y[50:90], y[:399], y[1:400],
+          "".join(rng.choice(list("ACGT"), size=77)), y[200:333] + "acgtn"]
+    for mode, omode in ((pkg.MODE_SAT_U8, o.MODE_SAT_U8), (pkg.MODE_EXACT, o.MODE_EXACT)):
+        engine.set_scoring_match(mode, 3, -3, 2)
+        engine.set_reference(y)
+        for batch in (xs, xs[:1], xs[:3], xs[3:4] * 5):
+            r = engine.align(batch, cons_stride=900)
+            for i, x in enumerate(batch):
+                w = o.align(x, y, mode=omode)
+                if w["score"] == 0:
+                    assert int(r["score"][i]) == 0 and int(r["len"][i]) == 0 and int(r["pos"][i]) == 0
+                    continue
+                _check(r, i, w, tag=("edge", mode, i, len(x)))
+    # reference shorter than the reads, one-column reference
+    for ref in ("ACGTTGCA", "G"):
+        engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
+        engine.set_reference(ref)
+        batch = ["TTACGTTGCATT", "GGGGGGGGGG", "ACGTTGCAA"]
+        r = engine.align(batch, cons_stride=64)
+        for i, x in enumerate(batch):
+            if len(x) == len(ref):
+                continue   # square input: reference defect (SURVEY F9)
+            _check(r, i, o.align(x, ref, mode=o.MODE_SAT_U8), tag=("short-ref", ref, i))
+
+
+def test_exact_mode_overflow_is_refused(engine, pkg):
+    """EXACT scores that could leave the 16-bit lanes are refused loudly, never computed wrongly."""
+    engine.set_scoring_match(pkg.MODE_EXACT, 100, -3, 2)
+    engine.set_reference("ACGT" * 200)
+    with pytest.raises(pkg.SwbError) as ei:
+        engine.align(["ACGT" * 150])
+    assert ei.value.code == -5
+    engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
+
+
+def test_chunked_custom_scoring_uses_default_for_the_final_alignment(engine, pkg):
+    """OMPParallelLocalAligner picks the piece with the constructor's scoring but re-aligns it with the
+    DEFAULT scoring (plocalaligner.cpp:135).  Batch of ragged reads, custom scoring, against the oracle."""
+    rng = np.random.default_rng(77)
+    y = "".join(rng.choice(list("ACGT"), size=2400))
+    xs = []
+    for m in (40, 40, 61, 61, 100, 100, 100, 33):
+        s0 = int(rng.integers(0, 2400 - m)); x = list(y[s0:s0 + m])
+        for q in range(m):
+            if rng.random() < 0.07:
+                x[q] = str(rng.choice(list("ACGT")))
+        xs.append("".join(x))
+    for mode, omode in ((pkg.MODE_SAT_U8, o.MODE_SAT_U8), (pkg.MODE_EXACT, o.MODE_EXACT)):
+        engine.set_scoring_match(mode, 5, -4, 3)
+        engine.set_reference(y)
+        r = engine.align(xs, npiece=5, ratio=2.0, cons_stride=600)
+        for i, x in enumerate(xs):
+            _check(r, i, o.align_chunked(x, y, 5, 2.0, mode=omode, match=5, mismatch=-4, gap=3), tag=("f8", mode, i))
+    engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
