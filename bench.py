@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=37888, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=151552, help="reads per GPU per step")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU-baseline sample (default 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

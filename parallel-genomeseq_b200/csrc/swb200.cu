@@ -105,6 +105,8 @@ struct swb_ctx {
   DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
   swb_stats stats{};
+  std::vector<cudaEvent_t> ev_pool;   // event pairs around every pass-2 launch of the current run
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -133,6 +135,13 @@ struct DebugTimer {
     t0 = t1;
   }
 };
+
+// pairs per sub-batch (see build_classes): four waves of 148 SMs x 4 CTAs x 16 pairs
+size_t chunk_pairs(const swb_ctx*) {
+  size_t v = 37888;
+  if (const char* e = getenv("SWB_CHUNK_PAIRS")) v = (size_t)std::max(64L, atol(e));
+  return v;
+}
 
 // Symbol-score selection of the kernels: "profile" = per-warp query profile in shared memory (one LDS per
 // cell pair, any scoring table), "compare" = HSET2 + LOP3 on packed symbols (match/mismatch scoring only).
@@ -318,6 +327,25 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
   // tasks in id order per class; remember ids for pairing
   std::vector<std::vector<uint32_t>> ids(out->size());
   for (size_t i = 0; i < seeds.size(); ++i) ids[cls[i]].push_back((uint32_t)i);
+  // Sub-batches: a class with more pairs than a few waves of the GPU is cut into consecutive sub-classes that
+  // run one after the other and reuse the same HBM work buffers, so the checkpoint period B (and with it the
+  // cost of pass 2) does not grow with the batch size.  Not for the chunked-reference path (piece selection
+  // needs every piece of a read in one class).
+  if (pieces == 1) {
+    const size_t chunk_tasks = 2 * chunk_pairs(ctx);
+    std::vector<LaunchClass> split;
+    std::vector<std::vector<uint32_t>> split_ids;
+    for (size_t c = 0; c < out->size(); ++c) {
+      const auto& id = ids[c];
+      for (size_t o = 0; o < id.size(); o += chunk_tasks) {
+        split.emplace_back();
+        split.back().geo = (*out)[c].geo; split.back().pieces = 1;
+        split_ids.emplace_back(id.begin() + o, id.begin() + std::min(id.size(), o + chunk_tasks));
+      }
+    }
+    out->swap(split);
+    ids.swap(split_ids);
+  }
   for (size_t c = 0; c < out->size(); ++c) {
     LaunchClass& lc = (*out)[c];
     const int L = lc.geo.L, R = lc.geo.R;
@@ -526,9 +554,11 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.counters = nullptr;
     tp.dbg_flags = getenv("SWB_DEBUG_FLAGS") ? atoi(getenv("SWB_DEBUG_FLAGS")) : 0;
     if (dbg.on) { CUDA_TRY(d_cnt.ensure(128)); CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 128, ctx->stream)); tp.counters = d_cnt.as<unsigned long long>(); }
-    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
+    CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     CUDA_TRY(launch_trace(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
-    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+    ctx->ev_used += 2;
     ctx->stats.kernel_launches++;
     dbg.mark("trace", L, R, (size_t)ntrace);
     if (dbg.on) {
@@ -574,6 +604,7 @@ void swb_destroy(swb_ctx* ctx) {
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
                     &ctx->d_len, &ctx->d_flags}) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -728,7 +759,8 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
   {
     size_t budget_mb = 8192;
     if (const char* e = getenv("SWB_CKPT_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
-    const double words_per_block = (double)((seeds.size() + 1) / 2) * ((double)max_m * 1.08 + 40.0) * (hs.mode == SWB_MODE_SAT_U8 ? 0.5 : 1.0);
+    const size_t pairs_in_flight = chunked ? (seeds.size() + 1) / 2 : std::min((seeds.size() + 1) / 2, chunk_pairs(ctx));
+    const double words_per_block = (double)pairs_in_flight * ((double)max_m * 1.08 + 40.0) * (hs.mode == SWB_MODE_SAT_U8 ? 0.5 : 1.0);
     int B = 32;
     ctx->C = 1;
     if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
@@ -771,8 +803,7 @@ int swb_batch_run(swb_ctx* ctx, float* device_us) {
   const bool chunked = ctx->npiece >= 1;
   const bool realign = chunked && !ctx->sc.is_default();
   CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
-  CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->ev_used = 0;
   if (!realign) {
     int rc = run_classes(ctx, ctx->classes.data(), ctx->classes.size(), false, chunked, true);
     if (rc) return rc;
@@ -807,7 +838,7 @@ int swb_batch_run(swb_ctx* ctx, float* device_us) {
   CUDA_TRY(cudaGetLastError());
   float ms = 0, ms2 = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-  CUDA_TRY(cudaEventElapsedTime(&ms2, ctx->ev[2], ctx->ev[3]));
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) { float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1])); ms2 += t; }
   const float total_us = ms * 1000.f;
   ctx->stats.pass2_us = ms2 * 1000.f;
   ctx->stats.pass1_us = total_us - ctx->stats.pass2_us;
