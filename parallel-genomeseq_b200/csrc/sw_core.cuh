@@ -364,10 +364,10 @@ struct Wavefront {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       upv[c] = __shfl_up_sync(0xffffffffu, st.bot[c], 1, L);
-      if (BND) {                                          // C == 1, L == 32: lane 0 works on column t
-        const int i = (t - 1) & 31;
-        if (i == 0) { chunk_cur = chunk_next; chunk_next = load_chunk(pd, ((t - 1) >> 5) + 1); }
-        const uint32_t north = __shfl_sync(0xffffffffu, chunk_cur, i);
+      if (BND) {                                          // L == 32: lane 0 works on columns C*(t-1)+1 .. C*t
+        const int base = C * (t - 1);                     // 0-based column of this step's first column
+        if (c == 0 && (base & 31) == 0) { chunk_cur = chunk_next; chunk_next = load_chunk(pd, (base >> 5) + 1); }
+        const uint32_t north = __shfl_sync(0xffffffffu, chunk_cur, (base & 31) + c);
         if (g == 0) upv[c] = north;
       } else {
         if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
@@ -375,10 +375,13 @@ struct Wavefront {
     }
     step<R, C, SAT>(st, sel, p.sc, upv, bmax, [&](int k, int c, uint32_t e_new) { hook(k, t, col_of<C>(t, g, c), e_new); });
     if (BND) {
-      const int j = col_of<C>(t, g, 0);
-      if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) {
-        bnd_out[j] = st.bot[0];
-        if (publish_to && ((j & 127) == 0 || j == (int)pd.n)) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)j; }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int j = col_of<C>(t, g, c);
+        if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) {
+          bnd_out[j] = st.bot[c];
+          if (publish_to && ((j & 127) == 0 || j == (int)pd.n)) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)j; }
+        }
       }
     }
   }
@@ -426,7 +429,7 @@ struct Wavefront {
   template <bool BND>
   __device__ __forceinline__ void begin(const PairDesc& pd, int t0) {
     restore(pd, t0);
-    if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
+    if (BND) chunk_next = load_chunk(pd, (C * t0) >> 5);  // B >= 32, so C * t0 is a multiple of 32
     prime(pd, t0 + 1);
   }
   // Pass-2 replay: a plain one-step loop (scores straight from the select, symbols one step ahead).  Pass 2
@@ -435,7 +438,7 @@ struct Wavefront {
   template <bool BND, class Hook>
   __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
     restore(pd, t0);
-    if (BND) chunk_next = load_chunk(pd, t0 >> 5);        // B >= 32, so t0 is a multiple of 32
+    if (BND) chunk_next = load_chunk(pd, (C * t0) >> 5);  // B >= 32, so C * t0 is a multiple of 32
     uint32_t bmax = NEG_INF2;
     uint32_t ynext[C], ynext2[C];                          // symbols of the next two steps (loads stay two steps ahead)
     load_symbols_m<true>(pd, t0 + 1, ynext);
@@ -463,7 +466,7 @@ struct Wavefront {
   template <class Hook>
   __device__ __forceinline__ void replay(const PairDesc& pd, bool multi, int t0, int t1, int nsteps, Hook&& hook) {
     bnd_out = nullptr; wait_on = nullptr; publish_to = nullptr;
-    if (C == 1 && multi) replay_impl<true>(pd, t0, t1, nsteps, hook);
+    if (multi) replay_impl<true>(pd, t0, t1, nsteps, hook);
     else replay_impl<false>(pd, t0, t1, nsteps, hook);
   }
 };
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   const int g = lane & (L - 1);
   const int groups_per_warp = 32 >> p.logL;
   uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
-  if (C == 1 && p.units) {
+  if (p.units) {
     // pipelined strips: this warp owns ONE strip of one pair.  Producers have lower unit indices than their
     // consumers, and thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
     if (gwarp >= p.nunits) return;
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   int n_min = (int)pd.n;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_min = min(n_min, __shfl_xor_sync(0xffffffffu, n_min, o));
-  if (C == 1 && nstrips > 1) {
+  if (nstrips > 1) {
     for (int s = 0; s < nstrips; ++s) {
       wf.prepare(pd, s, prof_warp);
       score_pass<R, C, SAT, PROFILE, true>(wf, p, pd, steps, n_min, live);
@@ -701,7 +704,8 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
             if (jmin <= jmax && imin <= imax) {
               const bool wraps = tp.mode == MODE_SAT_U8 && (jmax + imax >= ncols_raw);
               uint64_t lb;
-              if (tp.mode == MODE_SAT_U8) lb = wraps ? 0ull : ((uint64_t)(uint32_t)(jmin + imin) << 32);
+              // smallest raw column of the unit: d_min for ordinary cells, d_min - ncols (>= 0) for wrapped ones
+              if (tp.mode == MODE_SAT_U8) lb = (uint64_t)(uint32_t)(wraps ? max(0, jmin + imin - ncols_raw) : jmin + imin) << 32;
               else lb = (uint64_t)(uint32_t)jmin << 32;
               cand = (lb <= best) && (wraps == (phase == 0));
             }

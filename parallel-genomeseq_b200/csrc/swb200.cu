@@ -311,7 +311,6 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       // longer than one warp holds at the preferred rows-per-lane: row strips of 32 x R rows, processed top
       // to bottom (the strip count is per pair, so one launch class serves every length)
       g.L = 32; g.logL = 5; g.R = r_strip; g.nstrips = 0;     // 0 = "per pair"
-      if (ctx->C != 1) return fail(ctx, SWB_ERR_UNSUPPORTED, "row strips need SWB_COLS=1");
     }
     geo_by_m[kv.first] = g;
   }
@@ -469,7 +468,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
       // few long pairs: run the strips of a pair concurrently, one warp per (pair, strip) unit
       size_t total_units = 0;
       for (auto& pd : lc.pairs) total_units += pd.nstrips;
-      const bool pipelined = L == 32 && lc.max_strips > 1 && ctx->C == 1 && lc.pairs.size() < 148 * 8 && !getenv("SWB_NO_PIPELINE");
+      const bool pipelined = L == 32 && lc.max_strips > 1 && lc.pairs.size() < 148 * 8 && !getenv("SWB_NO_PIPELINE");
       pp.units = nullptr; pp.nunits = 0; pp.progress = nullptr; pp.abort_flag = nullptr;
       if (pipelined) {
         std::vector<uint2> units;
@@ -762,8 +761,11 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     const size_t pairs_in_flight = chunked ? (seeds.size() + 1) / 2 : std::min((seeds.size() + 1) / 2, chunk_pairs(ctx));
     const double words_per_block = (double)pairs_in_flight * ((double)max_m * 1.08 + 40.0) * (hs.mode == SWB_MODE_SAT_U8 ? 0.5 : 1.0);
     int B = 32;
-    ctx->C = 1;
-    if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
+    // columns per step: 1 everywhere (the software pipeline gives the ILP) except for few long pairs, where one
+    // warp per SM sub-partition is latency bound and two columns per step amortise the per-step latency
+    ctx->C = (!ctx->force_l32 && (seeds.size() + 1) / 2 < 148 * 8 && max_m > 1024) ? 2 : 1;
+    if (ctx->force_l32) ctx->C = 1;
+    else if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
     while (B < 65536 && words_per_block * 4.0 * ((double)max_n / ((double)B * ctx->C) + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
     ctx->B = B; ctx->logB = ilog2(B);
   }
