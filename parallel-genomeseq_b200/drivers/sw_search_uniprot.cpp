@@ -1,0 +1,99 @@
+// sw_search_uniprot — batched single-GPU replacement of the reference driver src/mpi_sw_solve_uniprot.cpp.
+//
+// What the reference does per worker rank (mpi_sw_solve_uniprot.cpp:95-138): for every database protein file,
+// SWAligner<Similarity_Matrix>(protein, query).calculateScore() — x = DB protein, y = query, exact (f32)
+// arithmetic, default scoring — and a record {char read[126], int pos_pred, double score} sent to the writer
+// rank, which prints "read,pos_pred,score" rows ("%.126s" of the protein, :132; header :151-156).
+// Here: the database is ONE multi-FASTA file (the 561 356 one-protein files become one blob +
+// offsets), all proteins go through ONE batched call, and the same CSV is written by the same process.
+// Several GPUs: run one process per GPU on a contiguous block of the database (sharding.block_partition).
+//   sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M]
+//     default scoring = the reference's (a == b ? 3 : -3, gap 2); --blosum62 10 tabulates BLOSUM62 through the
+//     callback constructor surface (smithwaterman.h:16-17) with linear gap 10.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../cpp/cuda_aligner.h"
+
+static const char* kOrder = "ARNDCQEGHILKMFPSTWYVBZX*";
+static const int kBlosum62[24][24] = {
+  { 4,-1,-2,-2, 0,-1,-1, 0,-2,-1,-1,-1,-1,-2,-1, 1, 0,-3,-2, 0,-2,-1, 0,-4}, {-1, 5, 0,-2,-3, 1, 0,-2, 0,-3,-2, 2,-1,-3,-2,-1,-1,-3,-2,-3,-1, 0,-1,-4},
+  {-2, 0, 6, 1,-3, 0, 0, 0, 1,-3,-3, 0,-2,-3,-2, 1, 0,-4,-2,-3, 3, 0,-1,-4}, {-2,-2, 1, 6,-3, 0, 2,-1,-1,-3,-4,-1,-3,-3,-1, 0,-1,-4,-3,-3, 4, 1,-1,-4},
+  { 0,-3,-3,-3, 9,-3,-4,-3,-3,-1,-1,-3,-1,-2,-3,-1,-1,-2,-2,-1,-3,-3,-2,-4}, {-1, 1, 0, 0,-3, 5, 2,-2, 0,-3,-2, 1, 0,-3,-1, 0,-1,-2,-1,-2, 0, 3,-1,-4},
+  {-1, 0, 0, 2,-4, 2, 5,-2, 0,-3,-3, 1,-2,-3,-1, 0,-1,-3,-2,-2, 1, 4,-1,-4}, { 0,-2, 0,-1,-3,-2,-2, 6,-2,-4,-4,-2,-3,-3,-2, 0,-2,-2,-3,-3,-1,-2,-1,-4},
+  {-2, 0, 1,-1,-3, 0, 0,-2, 8,-3,-3,-1,-2,-1,-2,-1,-2,-2, 2,-3, 0, 0,-1,-4}, {-1,-3,-3,-3,-1,-3,-3,-4,-3, 4, 2,-3, 1, 0,-3,-2,-1,-3,-1, 3,-3,-3,-1,-4},
+  {-1,-2,-3,-4,-1,-2,-3,-4,-3, 2, 4,-2, 2, 0,-3,-2,-1,-2,-1, 1,-4,-3,-1,-4}, {-1, 2, 0,-1,-3, 1, 1,-2,-1,-3,-2, 5,-1,-3,-1, 0,-1,-3,-2,-2, 0, 1,-1,-4},
+  {-1,-1,-2,-3,-1, 0,-2,-3,-2, 1, 2,-1, 5, 0,-2,-1,-1,-1,-1, 1,-3,-1,-1,-4}, {-2,-3,-3,-3,-2,-3,-3,-3,-1, 0, 0,-3, 0, 6,-4,-2,-2, 1, 3,-1,-3,-3,-1,-4},
+  {-1,-2,-2,-1,-3,-1,-1,-2,-2,-3,-3,-1,-2,-4, 7,-1,-1,-4,-3,-2,-2,-1,-2,-4}, { 1,-1, 1, 0,-1, 0, 0, 0,-1,-2,-2, 0,-1,-2,-1, 4, 1,-3,-2,-2, 0, 0, 0,-4},
+  { 0,-1, 0,-1,-1,-1,-1,-2,-2,-1,-1,-1,-1,-2,-1, 1, 5,-2,-2, 0,-1,-1, 0,-4}, {-3,-3,-4,-4,-2,-2,-3,-2,-2,-3,-2,-3,-1, 1,-4,-3,-2,11, 2,-3,-4,-3,-2,-4},
+  {-2,-2,-2,-3,-2,-1,-2,-3, 2,-1,-1,-2,-1, 3,-3,-2,-2, 2, 7,-1,-3,-2,-1,-4}, { 0,-3,-3,-3,-1,-2,-2,-3,-3, 3, 1,-2, 1,-1,-2,-2, 0,-3,-1, 4,-3,-2,-1,-4},
+  {-2,-1, 3, 4,-3, 0, 1,-1, 0,-3,-4, 0,-3,-3,-2, 0,-1,-4,-3,-3, 4, 1,-1,-4}, {-1, 0, 0, 1,-3, 3, 4,-2, 0,-3,-3, 1,-1,-3,-1, 0,-1,-3,-2,-2, 1, 4,-1,-4},
+  { 0,-1,-1,-1,-2,-1,-1,-1,-1,-1,-1,-1,-1,-1,-2, 0, 0,-2,-1,-1,-1,-1,-1,-4}, {-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4, 1}};
+
+static bool read_fasta_records(const std::string& path, std::vector<std::string>* seqs) {
+  std::ifstream f(path);
+  if (!f) return false;
+  std::string line, cur;
+  bool open = false;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (!line.empty() && line[0] == '>') { if (open) seqs->push_back(cur); cur.clear(); open = true; continue; }
+    if (!open) { open = true; }         // header-less file: one record
+    cur += line;
+  }
+  if (open) seqs->push_back(cur);
+  return true;
+}
+
+int main(int argc, char** argv) {
+  std::vector<std::string> pos;
+  bool blosum = false; float gap = 2.f; size_t first = 0, count = (size_t)-1;
+  for (int i = 1; i < argc; ++i) {
+    if (!std::strcmp(argv[i], "--blosum62") && i + 1 < argc) { blosum = true; gap = (float)std::atof(argv[++i]); }
+    else if (!std::strcmp(argv[i], "--first") && i + 1 < argc) first = (size_t)std::atoll(argv[++i]);
+    else if (!std::strcmp(argv[i], "--count") && i + 1 < argc) count = (size_t)std::atoll(argv[++i]);
+    else pos.push_back(argv[i]);
+  }
+  if (pos.size() < 3) { std::cerr << "usage: sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M]" << std::endl; return 2; }
+  std::vector<std::string> q, db;
+  if (!read_fasta_records(pos[0], &q) || q.empty()) { std::cerr << "cannot read query " << pos[0] << std::endl; return 2; }
+  if (!read_fasta_records(pos[1], &db) || db.empty()) { std::cerr << "cannot read database " << pos[1] << std::endl; return 2; }
+  const std::string& fa_string = q[0];
+  if (first > db.size()) first = db.size();
+  if (count > db.size() - first) count = db.size() - first;
+  std::vector<std::string_view> xs;
+  for (size_t i = first; i < first + count; ++i) xs.emplace_back(db[i]);
+
+  swb::CUDABatchAligner aligner(SWB_MODE_EXACT);
+  aligner.set_reference(fa_string);
+  if (blosum) {
+    aligner.set_scoring([](const char& a, const char& b) -> float {
+      const char* pa = std::strchr(kOrder, a); const char* pb = std::strchr(kOrder, b);
+      if (!pa || !pb || !a || !b) return -4.f;
+      return (float)kBlosum62[pa - kOrder][pb - kOrder];
+    }, gap);
+  } else {
+    aligner.set_scoring(3.f, -3.f, 2.f);
+  }
+  swb::CUDABatchAligner::Out out;
+  try { out = aligner.align(xs, 0, 0.f, /*consensus=*/false); }
+  catch (const swb::Error& e) { std::cerr << "search failed: " << e.what() << std::endl; return 1; }
+
+  std::ofstream csv(pos[2]);
+  csv << "read,pos_pred,score\n";
+  unsigned long long cells = 0;
+  char buff[127];
+  for (size_t i = 0; i < xs.size(); ++i) {
+    std::snprintf(buff, sizeof buff, "%.126s", db[first + i].c_str());
+    csv << buff << ", " << (int)out.pos[i] << ", " << (double)out.score[i] << "\n";
+    cells += (unsigned long long)xs[i].size() * fa_string.size();
+  }
+  std::cout << "Searched " << xs.size() << " proteins against a " << fa_string.size() << "-residue query: device time "
+            << out.device_us * 1e-3 << " ms, GCUPS " << cells / (double)out.device_us * 1e-3 << std::endl;
+  return 0;
+}

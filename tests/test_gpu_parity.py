@@ -319,3 +319,41 @@ def test_chunked_custom_scoring_uses_default_for_the_final_alignment(engine, pkg
         for i, x in enumerate(xs):
             _check(r, i, o.align_chunked(x, y, 5, 2.0, mode=omode, match=5, mismatch=-4, gap=3), tag=("f8", mode, i))
     engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
+
+
+def test_drivers_sw_solve_big_and_uniprot_search(tmp_path, data_small, c4_sample):
+    """The two other batched drivers: sw_solve_big (single-line reference, nrepeat min-of-N, [INFO]
+    GCUPS lines; npiece=2 means 4 pieces like sw_solve_big.cpp:78) and the UniProt search (multi-FASTA database,
+    'read,pos_pred,score' rows like mpi_sw_solve_uniprot.cpp:151-168) against the reference's goldens."""
+    import os
+    import subprocess
+    from conftest import ROOT, GOLDEN
+    ddir = os.path.join(ROOT, "parallel-genomeseq_b200", "drivers")
+    if not (os.path.isfile(os.path.join(ddir, "sw_solve_big")) and os.path.isfile(os.path.join(ddir, "sw_search_uniprot"))):
+        subprocess.check_call(["make", "-C", ddir])
+    ref, truth = data_small
+    fa = tmp_path / "custom_ref_1.fa"
+    fa.write_text(ref + "\n")
+    reads_csv = os.path.join(GOLDEN, "data_small", "data_small_ground_truth.csv")
+    for args, gold in ((["0", "2"], "data_small_sw_skewed.csv"), (["2", "3"], "data_small_p4.csv")):
+        r = subprocess.run([os.path.join(ddir, "sw_solve_big")] + args + ["--fa", str(fa), "--reads", reads_csv], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "GCUPS avg:" in r.stdout and "[INFO] Average SW iter_ad_read times:" in r.stdout
+        g0 = read_golden_csv(gold)[0]
+        assert f"[INFO] first read: pos {g0['pos']} score {g0['score']}" in r.stdout, r.stdout
+    q = tmp_path / "query.fasta"
+    q.write_text(">query\n" + c4_sample["query"] + "\n")
+    db = tmp_path / "db.fasta"
+    with open(db, "w") as f:
+        for k, e in enumerate(c4_sample["entries"]):
+            f.write(f">sp|P{k:05d}|synthetic\n")
+            for o_ in range(0, len(e["x"]), 60):
+                f.write(e["x"][o_:o_ + 60] + "\n")
+    out_csv = tmp_path / "out.csv"
+    r = subprocess.run([os.path.join(ddir, "sw_search_uniprot"), str(q), str(db), str(out_csv), "--blosum62", str(c4_sample["gap"])], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "GCUPS" in r.stdout, r.stdout + r.stderr
+    rows = out_csv.read_text().strip().split("\n")
+    assert rows[0] == "read,pos_pred,score" and len(rows) == len(c4_sample["entries"]) + 1
+    for line, e in zip(rows[1:], c4_sample["entries"]):
+        f_ = line.split(", ")
+        assert f_[0] == e["x"][:126] and int(f_[1]) == e["pos"] and float(f_[2]) == e["score"]
