@@ -808,9 +808,10 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
           const int gg = il2 / R;
           return scr + slot(step_of<C>(j, gg), (j - 1) % C, il2 - gg * R, gg);
         };
-        // The walk is a chain of dependent loads; most moves are diagonal, so the three neighbours of the next
-        // SPEC cells along the diagonal are loaded together and consumed while the walk stays on the diagonal.
-        constexpr int SPEC = 4;
+        // The walk is a chain of dependent loads.  The three neighbours (and the two consensus characters) of a
+        // cell are loaded as one batch; SPEC > 1 would also fetch the next cells along the diagonal speculatively,
+        // but with every SM full of walkers the extra loads cost more than the saved round trips (measured).
+        constexpr int SPEC = 1;
         int v1[SPEC], v2[SPEC], v3[SPEC];
         uint8_t xb[SPEC], yb[SPEC];                          // x[ix-d-1], y[iy-d-1]: the characters the consensus emits
         int have = 0, at = 0;                                // v*[at] belongs to the current cell when at < have
