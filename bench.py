@@ -62,8 +62,8 @@ def load_traffic(n_reads):
                 with open(os.path.join(prof, fn)) as f:
                     k = json.load(f)["score_kernel"]
                 if k["reads_per_gpu"] == n_reads:
-                    return k["dram_bytes_read"] + k["dram_bytes_write"]
-    return None
+                    return k["dram_bytes_read"] + k["dram_bytes_write"], k.get("alu_pipe_busy")
+    return None, None
 
 
 class ClockSampler:
@@ -251,12 +251,12 @@ def main():
     h2d = blob_np.nbytes + offs_np.nbytes
     d2h = n_reads * (4 + 4 + 8 + 4 + 4) + 2 * n_reads * cons_stride
     for _ in range(2):
-        eng.align((blob_np, offs_np), consensus=True, cons_stride=cons_stride)
+        eng.align((blob_np, offs_np), consensus=True, cons_stride=cons_stride, decode=False)
     barrier()
     e2e_t = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        out = eng.align((blob_np, offs_np), consensus=True, cons_stride=cons_stride)
+        out = eng.align((blob_np, offs_np), consensus=True, cons_stride=cons_stride, decode=False)
         if use_dist:
             gather_results()
         torch.cuda.synchronize()
@@ -277,6 +277,7 @@ def main():
 
     if rank == 0:
         ops = OPS_PER_CELL["SAT_U8"]
+        traffic, alu_busy = load_traffic(n_reads)
         k_gcups = cells_step / (pass1_us * 1e-6) / 1e9          # dominant kernel (score pass), this GPU
         achieved = k_gcups * 1e9 * ops / 1e12                    # algorithmic Tops/s
         hbm_bytes = h2d + st["cells_executed"] / (2 * st["rows_per_lane"] * st["block_steps"]) * (st["rows_per_lane"] + 2) * 4  # checkpoints + block maxima
@@ -292,7 +293,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": p_int, "unit": "Tops/s (int lane-ops)", "frac": achieved / p_int,
-                         "traffic": load_traffic(n_reads), "traffic_unit": "bytes per score_kernel launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "ops_per_cell": ops, "kernel": "score_kernel (pass 1)", "kernel_gcups": k_gcups, "kernel_ms": pass1_us / 1e3,
+                         "traffic": traffic, "traffic_unit": "bytes per score_kernel launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "alu_pipe_busy_ncu": alu_busy, "ops_per_cell": ops, "kernel": "score_kernel (pass 1)", "kernel_gcups": k_gcups, "kernel_ms": pass1_us / 1e3,
                          "kernel_share_of_step": pass1_us / step_us, "peak_source": p_src,
                          "executed_cell_fraction": cells_step / max(1, st["cells_executed"]),
                          "hbm": {"achieved_gbs": hbm_bytes / (pass1_us * 1e-6) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src}},

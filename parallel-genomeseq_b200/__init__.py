@@ -188,17 +188,24 @@ class Engine:
         return out
 
     # ---- one-call API (host buffers in, host buffers out) ----------------------------------------------
-    def align(self, seqs, npiece=0, ratio=0.0, consensus=True, cons_stride=None):
-        """Returns dict(score, pos, end, len, flags, cx, cy, device_us); cx/cy are lists of str (end -> start)."""
+    def align(self, seqs, npiece=0, ratio=0.0, consensus=True, cons_stride=None, decode=True):
+        """Returns dict(score, pos, end, len, flags, cx, cy, device_us); cx/cy are lists of str (end -> start).
+        decode=False skips the per-read Python string decoding and returns the raw arenas as cx_raw / cy_raw."""
         blob, offs = seqs if isinstance(seqs, tuple) else pack_sequences(seqs)
         n = len(offs) - 1
         if cons_stride is None:
             cons_stride = int(2 * np.diff(offs).astype(np.int64).max() + 64)
         flags = FLAG_CONSENSUS if consensus else 0
+        # the consensus arenas (~100 MB for a large batch) are kept between calls of the same shape — re-allocating
+        # them per call costs page faults inside the end-to-end time; cx_raw / cy_raw are therefore only valid
+        # until the next align() of the same shape.  The small per-read arrays are fresh on every call.
         out = dict(score=np.zeros(n, np.int32), pos=np.zeros(n, np.uint32), end=np.zeros((n, 2), np.uint32),
                    len=np.zeros(n, np.uint32), flags=np.zeros(n, np.uint32))
-        cx = np.zeros((n, cons_stride), np.uint8) if consensus else None
-        cy = np.zeros((n, cons_stride), np.uint8) if consensus else None
+        key = (n, cons_stride)
+        if consensus and getattr(self, "_arena_key", None) != key:
+            self._arena_key = key
+            self._arena = (np.zeros((n, cons_stride), np.uint8), np.zeros((n, cons_stride), np.uint8))
+        cx, cy = self._arena if consensus else (None, None)
         us = C.c_float(0)
         self._check(self.lib.swb_align_batch(self.h, blob.ctypes.data, offs.ctypes.data, n, int(npiece), float(ratio), flags,
                                              out["score"].ctypes.data, out["pos"].ctypes.data, out["end"].ctypes.data,
@@ -206,7 +213,8 @@ class Engine:
                                              out["len"].ctypes.data, cons_stride, out["flags"].ctypes.data, C.byref(us)))
         self.n_seqs, self.cons_stride, self.flags = n, cons_stride, flags
         out["device_us"] = us.value
-        if consensus:
+        out["cx_raw"], out["cy_raw"] = cx, cy
+        if consensus and decode:
             out["cx"] = [cx[i, :min(out["len"][i], cons_stride)].tobytes().decode("latin-1") for i in range(n)]
             out["cy"] = [cy[i, :min(out["len"][i], cons_stride)].tobytes().decode("latin-1") for i in range(n)]
         return out

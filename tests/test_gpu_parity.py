@@ -357,3 +357,34 @@ def test_drivers_sw_solve_big_and_uniprot_search(tmp_path, data_small, c4_sample
     for line, e in zip(rows[1:], c4_sample["entries"]):
         f_ = line.split(", ")
         assert f_[0] == e["x"][:126] and int(f_[1]) == e["pos"] and float(f_[2]) == e["score"]
+
+
+def test_driver_fine_grain_benchmark_surface(tmp_path):
+    """omp_sw_solve_small replacement: same argv, align-output rows and timing-CSV schema
+    (omp_sw_solve_small.cpp:66-73,233-239); long reads (row strips) in both arithmetic flavours vs the oracle."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    drv = os.path.join(ROOT, "parallel-genomeseq_b200", "drivers", "omp_sw_solve_small")
+    if not os.path.isfile(drv):
+        subprocess.check_call(["make", "-C", os.path.dirname(drv)])
+    ref = synth.c3_reference(20_000, seed=5)
+    reads = synth.mutated_reads(ref, 3, 3_000, seed=6, sub=0.02, ins=0.002, dele=0.002)
+    fa = tmp_path / "ref.fa"
+    fa.write_text(ref[:9000] + "\n" + ref[9000:] + "\n")          # every line is concatenated, no header
+    rcsv = tmp_path / "reads.csv"
+    rcsv.write_text("index,QNAME,SEQ,POS\n" + "".join(f"{i},r{i},{x},0\n" for i, x in enumerate(reads)))
+    timing = tmp_path / "timing.csv"
+    for fg, omode in ((1, o.MODE_EXACT), (-1, o.MODE_SAT_U8)):
+        out_csv = tmp_path / f"align_{fg}.csv"
+        r = subprocess.run([drv, "solve_small", "2", "4", str(fg), str(timing), str(fa), str(rcsv), str(out_csv)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "GCUPS" in r.stdout, r.stdout + r.stderr
+        rows = out_csv.read_text().strip().split("\n")
+        assert rows[0] == "index,QNAME,SEQ,POS,pos_pred,score" and len(rows) == 3      # the first n_reads = 2 reads
+        for line, x in zip(rows[1:], reads):
+            w = o.align(x, ref, mode=omode)
+            f_ = line.split(", ")
+            assert int(f_[-2]) == w["pos"] and float(f_[-1]) == w["score"]
+    t = timing.read_text().strip().split("\n")
+    assert t[0] == "n_reads,n_threads,finegrain_type,avg_t_calcscore,avg_t_adread,avg_t_adisum" and len(t) == 3
+    assert t[1].startswith("2,4,1,") and t[2].startswith("2,4,-1,")
