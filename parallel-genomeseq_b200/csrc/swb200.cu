@@ -763,7 +763,8 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     int B = 32;
     // columns per step: 1 everywhere (the software pipeline gives the ILP) except for few long pairs, where one
     // warp per SM sub-partition is latency bound and two columns per step amortise the per-step latency
-    ctx->C = (!ctx->force_l32 && (seeds.size() + 1) / 2 < 148 * 8 && max_m > 1024) ? 2 : 1;
+    // (few long pairs), and for batches too small to put more than one warp on an SM sub-partition
+    ctx->C = (!ctx->force_l32 && (((seeds.size() + 1) / 2 < 148 * 8 && max_m > 1024) || (seeds.size() + 1) / 2 <= 148 * 4)) ? 2 : 1;
     if (ctx->force_l32) ctx->C = 1;
     else if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
     while (B < 65536 && words_per_block * 4.0 * ((double)max_n / ((double)B * ctx->C) + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
