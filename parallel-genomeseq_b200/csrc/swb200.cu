@@ -658,7 +658,7 @@ int swb_set_scoring_match(swb_ctx* ctx, int mode, float match, float mismatch, f
 int swb_set_reference(swb_ctx* ctx, const char* y, size_t n) {
   if (!ctx || (!y && n)) return SWB_ERR_ARG;
   if (n == 0) return fail(ctx, SWB_ERR_ARG, "empty reference");
-  if (n > 0x7FFF0000ull) return fail(ctx, SWB_ERR_UNSUPPORTED, "reference longer than 2^31");
+  if (n > 0x7FF00000ull) return fail(ctx, SWB_ERR_UNSUPPORTED, "reference longer than 2^31 - 2^20 (step counters are 32-bit)");
   CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->y.assign((const uint8_t*)y, (const uint8_t*)y + n);
   memset(ctx->code_of, 0xFF, sizeof ctx->code_of);
