@@ -296,24 +296,34 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= want) r_strip = kRSet[i];
     }
   }
-  // ragged batches (a protein database): one strip-geometry class for every length instead of a launch class
-  // per (L, R) combination — a single score launch and a single trace launch, longest sequences first
-  const bool ragged = count_by_m.size() > 8;
-  if (ragged && !getenv("SWB_STRIP_R")) {
+  // Geometry per distinct length.  First pass: the best (L, R) for every length on its own.
+  const int r_cap = profile ? std::max(r_pref, kRSet[0]) : 32;
+  std::map<std::pair<int, int>, size_t> tasks_per_geo;
+  for (auto& kv : count_by_m) {
+    Geometry g;
+    if (ctx->force_l32 || (int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
+      g.L = 32; g.logL = 5; g.R = 0; g.nstrips = 0;     // R = 0: strip geometry, filled in below
+    }
+    geo_by_m[kv.first] = g;
+    tasks_per_geo[std::make_pair(g.L, g.R)] += kv.second;
+  }
+  // Ragged batches (a protein database): (L, R) classes that hold only a sliver of the batch would each cost
+  // their own short launches; they are folded into ONE strip-geometry class (32 lanes x thin strips, strip
+  // count per pair, longest sequences first).  Classes that hold a real share of the batch keep their geometry
+  // (reads trimmed to 100..150 bp still run as 8 x 16 and 8 x 19).
+  const size_t small_class = std::max<size_t>(1024, seeds.size() / 50);
+  size_t folded = 0;
+  if (tasks_per_geo.size() > 2)
+    for (auto& kv : geo_by_m) {
+      Geometry& g = kv.second;
+      if (g.R != 0 && tasks_per_geo[std::make_pair(g.L, g.R)] < small_class) { g.L = 32; g.logL = 5; g.R = 0; g.nstrips = 0; ++folded; }
+    }
+  if (folded > 0 && !getenv("SWB_STRIP_R")) {
     const int cap = 4;      // thin strips: pass 2 replays O(rows-in-strip) columns per strip (measured best on B200)
     r_strip = kRSet[0];
     for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= cap && kRSet[i] <= r_hard) r_strip = kRSet[i];
   }
-  for (auto& kv : count_by_m) {
-    Geometry g;
-    const int r_cap = profile ? std::max(r_pref, kRSet[0]) : 32;
-    if (ctx->force_l32 || ragged || (int)kv.first > 32 * r_strip || !choose_geometry((int)kv.first, (seeds.size() + 1) / 2, r_cap, &g)) {
-      // longer than one warp holds at the preferred rows-per-lane: row strips of 32 x R rows, processed top
-      // to bottom (the strip count is per pair, so one launch class serves every length)
-      g.L = 32; g.logL = 5; g.R = r_strip; g.nstrips = 0;     // 0 = "per pair"
-    }
-    geo_by_m[kv.first] = g;
-  }
+  for (auto& kv : geo_by_m) if (kv.second.R == 0) kv.second.R = r_strip;
   std::map<std::pair<int, int>, int> class_of;   // (L, R) -> class index
   std::vector<int> cls(seeds.size());
   for (size_t i = 0; i < seeds.size(); i += (size_t)pieces) {
@@ -461,6 +471,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
       const size_t per_warp = (size_t)ctx->KP * R * 32 * 4;
       while (warps_per_cta > 1 && per_warp * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
       smem = per_warp * warps_per_cta;
+      if (const char* e = getenv("SWB_EXTRA_SMEM")) smem += (size_t)atol(e);   // occupancy experiments
     }
     const int groups_per_warp = 32 / L;
     {

@@ -388,3 +388,21 @@ def test_driver_fine_grain_benchmark_surface(tmp_path):
     t = timing.read_text().strip().split("\n")
     assert t[0] == "n_reads,n_threads,finegrain_type,avg_t_calcscore,avg_t_adread,avg_t_adisum" and len(t) == 3
     assert t[1].startswith("2,4,1,") and t[2].startswith("2,4,-1,")
+
+
+def test_ragged_read_lengths_keep_efficient_geometry(engine, pkg):
+    """Reads trimmed to 100..150 bp (many distinct lengths) must keep the sub-warp geometries (8 x 16 / 8 x 19),
+    not fall back to thin strips, and stay bit-exact."""
+    rng = np.random.default_rng(41)
+    y = "".join(rng.choice(list("ACGT"), size=30_000))
+    xs = []
+    for k in range(6000):
+        m = int(rng.integers(100, 151)); s0 = int(rng.integers(0, 30_000 - m))
+        xs.append(y[s0:s0 + m])
+    engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
+    engine.set_reference(y)
+    r = engine.align(xs, consensus=True)
+    st = engine.stats()
+    assert st["lanes_per_pair"] == 8 and st["rows_per_lane"] in (16, 19), st
+    for i in range(0, len(xs), 37):
+        _check(r, i, o.align(xs[i], y, mode=o.MODE_SAT_U8), tag=("ragged", i, len(xs[i])))
