@@ -406,3 +406,16 @@ def test_ragged_read_lengths_keep_efficient_geometry(engine, pkg):
     assert st["lanes_per_pair"] == 8 and st["rows_per_lane"] in (16, 19), st
     for i in range(0, len(xs), 37):
         _check(r, i, o.align(xs[i], y, mode=o.MODE_SAT_U8), tag=("ragged", i, len(xs[i])))
+
+
+def test_randomised_fuzz_against_oracle():
+    """tools/fuzz_parity.py: random shapes (1..3500 columns, 1..2600 rows incl. row strips), alphabets, match and
+    tabulated scorings (incl. zero gap / zero mismatch), both modes, chunking, and kernel knobs (select, columns
+    per step, sub-batch size) against the oracle.  Longer runs: `python tools/fuzz_parity.py 1500 <seed>`."""
+    import os
+    import subprocess
+    import sys as _sys
+    from conftest import ROOT
+    env = {k: v for k, v in os.environ.items() if not k.startswith("SWB_")}
+    r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "200", "777"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout + r.stderr
