@@ -306,6 +306,7 @@ struct Wavefront {
   uint32_t* bnd_out = nullptr;        // boundary row below this strip, null for the last strip
   uint32_t chunk_cur = 0, chunk_next = 0;
   volatile const uint32_t* wait_on = nullptr;   // progress counter of the strip above (pipelined strips)
+  mutable uint32_t seen_progress = 0;           // last value read from *wait_on
   uint32_t* publish_to = nullptr;               // this strip's progress counter
   __device__ __forceinline__ Wavefront(const PassParams& p_) : p(p_) {}
 
@@ -339,11 +340,12 @@ struct Wavefront {
   __device__ __forceinline__ uint32_t load_chunk(const PairDesc& pd, int k) const {
     const int j = 32 * k + 1 + lane;
     if (wait_on && bnd_in) {
-      // pipelined strips: wait until the strip above has published the last column of this chunk
+      // pipelined strips: wait until the strip above has published the last column of this chunk.  The last
+      // value read from the progress counter is remembered, so most chunks need no poll at all.
       const uint32_t need = (uint32_t)min((int)pd.n, 32 * k + 32);
-      if (32 * k + 1 <= (int)pd.n) {
+      if (32 * k + 1 <= (int)pd.n && seen_progress < need) {
         unsigned spins = 0;
-        while (*wait_on < need) {
+        while ((seen_progress = *wait_on) < need) {
           __nanosleep(400);
           if (++spins > (1u << 24)) { if (p.abort_flag) *p.abort_flag = 1u; break; }
         }
@@ -380,7 +382,7 @@ struct Wavefront {
         const int j = col_of<C>(t, g, c);
         if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) {
           bnd_out[j] = st.bot[c];
-          if (publish_to && ((j & 127) == 0 || j == (int)pd.n)) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)j; }
+          if (publish_to && ((j & 511) == 0 || j == (int)pd.n)) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)j; }
         }
       }
     }
