@@ -375,7 +375,7 @@ struct Wavefront {
         if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
       }
     }
-    step<R, C, SAT>(st, sel, p.sc, upv, bmax, [&](int k, int c, uint32_t e_new) { hook(k, t, col_of<C>(t, g, c), e_new); });
+    step<R, C, SAT>(st, sel, p.sc, upv, bmax, [&](int k, int c, uint32_t e_new) { hook(k, c, t, col_of<C>(t, g, c), e_new); });
     if (BND) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -400,7 +400,7 @@ struct Wavefront {
       load_symbols_m<true>(pd, t + 1, py1);               // py1 = symbols of step t+1
     }
   }
-  // steps t and t+1; hook(k, step, j, E_new)
+  // steps t and t+1; hook(k, c, step, j, E_new)
   template <bool MASKED, bool BND, class Hook>
   __device__ __forceinline__ void two_steps(const PairDesc& pd, int t, uint32_t& bmax, Hook&& hook) {
     if (PROFILE) {
@@ -452,7 +452,7 @@ struct Wavefront {
       for (int c = 0; c < C; ++c) { ycur[c] = ynext[c]; ynext[c] = ynext2[c]; }
       load_symbols_m<true>(pd, t + 2, ynext2);
       const bool on = t <= t1;
-      auto h = [&](int k, int, int j, uint32_t e_new) { if (on) hook(k, j, e_new); };
+      auto h = [&](int k, int c, int tt, int j, uint32_t e_new) { if (on) hook(k, c, tt, j, e_new); };
       if (PROFILE) {
 #pragma unroll
         for (int c = 0; c < C; ++c) psel.set_column(c, ycur[c]);
@@ -485,7 +485,7 @@ __device__ __forceinline__ void score_pass(Wavefront<R, C, SAT, PROFILE>& wf, co
   uint32_t* ck = p.ckpt + pd.ck_off;
   wf.template begin<BND>(pd, 0);
   uint32_t bmax = NEG_INF2;
-  auto nohook = [](int, int, int, uint32_t) {};
+  auto nohook = [](int, int, int, int, uint32_t) {};
   const int nb = steps >> p.logB;
   for (int b = 0; b < nb; ++b) {
     const int t0 = b << p.logB;
@@ -571,8 +571,8 @@ struct TraceParams {
   int ntasks;
   int mode;                   // MODE_SAT_U8: skewed raw-order tie-break; MODE_EXACT: column-major
   int max_pos;                // largest positive substitution score: a cell of score V needs row >= ceil(V / max_pos)
-  uint32_t* scratch;          // per group: ring of the last Wc steps, word (((t & (Wc-1)) * C + c) * R + k) * L + g
-  int Wc, rstride;            // ring depth in steps (power of two); rstride = C * R * L words per step
+  uint32_t* scratch;          // per warp: ring of the last Wc steps, word (((t & (Wc-1)) * C + c) * R + k) * 32 + lane
+  int Wc, rstride;            // ring depth in steps (power of two); rstride = C * R * L words per step and group
   int32_t* out_score;
   uint32_t* out_pos;
   uint32_t* out_end;          // 2 per task: index_x, index_y of the arg-max
@@ -582,7 +582,7 @@ struct TraceParams {
   uint32_t cons_cap;          // bytes per task in out_cx / out_cy
   uint32_t* out_flags;        // bit0: consensus overflowed cons_cap
   int want_consensus;
-  int dbg_flags;                  // diagnostics: bit0 skip ring stores, bit1 skip the walk (results are then wrong)
+  int dbg_flags;                  // diagnostics: bit1 skip the walk (results are then wrong)
   unsigned long long* counters;   // diagnostics (SWB_DEBUG): [0] scan replays, [1] sessions, [2] scan lockstep rounds, [3] session rounds, [4] session steps (warp max)
 };
 
@@ -631,7 +631,11 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int ggroup = gwarp * groups_per_warp + grp_in_warp;
-  uint32_t* scr = tp.scratch + (size_t)ggroup * tp.Wc * tp.rstride;   // ring of recomputed steps, lane-contiguous words
+  // ring of recomputed steps, one per warp: word (((t & (Wc-1)) * C + c) * R + k) * 32 + lane, so the 32 lanes of a
+  // store are contiguous and every offset inside a step is a compile-time constant (groups of a warp may sit at
+  // different steps t; they write disjoint lanes of different ring rows)
+  constexpr uint32_t RING_STEP = (uint32_t)(C * R * 32);
+  uint32_t* scr = tp.scratch + (size_t)gwarp * tp.Wc * RING_STEP;
   const int wmask = tp.Wc - 1;
   const int G = p.sc.G;
   const int S = L * R;                 // rows per strip
@@ -729,7 +733,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       if (multi && us != cur_strip) { cur_strip = us; wf.prepare(pd, us, prof_warp); }
       const int row0 = cur_strip * S + g * R + 1;
       uint64_t mine = ~0ull;
-      wf.replay(pd, multi, t0, has ? t0 + p.B : -1, p.B, [&](int k, int j, uint32_t e_new) {
+      wf.replay(pd, multi, t0, has ? t0 + p.B : -1, p.B, [&](int k, int, int, int j, uint32_t e_new) {
         if (((e_new ^ vmax2) & hmask) == 0) {
           const int i = row0 + k;
           if (i <= m && j >= 1 && j <= n) {
@@ -781,8 +785,8 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       const int t_lo = done ? 0 : (((c_lo / C) >> p.logB) << p.logB);
       const int valid_lo = max(C * t_lo, C * (t_hi - tp.Wc) + 1);   // oldest column every lane still holds
       if (multi && !done && ss != cur_strip) { cur_strip = ss; wf.prepare(pd, ss, prof_warp); }
-      // ring slot of (step t, column-in-step c, row-in-lane k, lane g): all 32 lanes of a store are contiguous
-      auto slot = [&](int t, int c, int k, int gg) -> size_t { return ((size_t)((t & wmask) * C + c) * R + k) * L + gg; };
+      // ring slot of (step t, column-in-step c, row-in-lane k, lane gg of this group)
+      auto slot = [&](int t, int c, int k, int gg) -> uint32_t { return (uint32_t)(t & wmask) * RING_STEP + (uint32_t)((c * R + k) * 32) + gshift + (uint32_t)gg; };
       if (!done && t_lo > 0) {
         // the checkpoint itself is the last column of step t_lo for every lane
         const uint32_t* ck = p.ckpt + pd.ck_off + wf.ck_index(pd, (t_lo >> p.logB) - 1);
@@ -791,9 +795,10 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       }
       const int nsteps = warp_max_i32(t_hi - t_lo);
       if (tp.counters) { if (!done && g == 0) atomicAdd(tp.counters + 1, 1ull); if (lane == 0) { atomicAdd(tp.counters + 3, 1ull); atomicAdd(tp.counters + 4, (unsigned long long)nsteps); } }
-      wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int j, uint32_t e_new) {
-        // column j of lane g belongs to step g + ceil(j / C); virtual columns j <= 0 hold H = 0 and are never read
-        if (j >= 1 && !(tp.dbg_flags & 1)) scr[slot(step_of<C>(j, g), (j - 1) % C, k, g)] = e_new;
+      uint32_t* const scr_lane = scr + lane;
+      wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int c, int t, int j, uint32_t e_new) {
+        // lane g computes column j in step t = g + ceil(j / C); virtual columns j <= 0 hold H = 0 and are never read
+        if (j >= 1) (scr_lane + (uint32_t)(t & wmask) * RING_STEP)[(c * R + k) * 32] = e_new;
       });
       __syncwarp();
       if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 12, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
@@ -904,7 +909,7 @@ __global__ void __launch_bounds__(128) dump_kernel(const DumpParams dp) {
   for (int s = 0; s < (int)pd.nstrips; ++s) {
     wf.prepare(pd, s, smem_prof);
     const int row0 = s * S + g * R + 1;
-    wf.replay(pd, multi, 0, steps, steps, [&](int k, int j, uint32_t e_new) {
+    wf.replay(pd, multi, 0, steps, steps, [&](int k, int, int, int j, uint32_t e_new) {
       const int i = row0 + k;
       if (i <= dp.m && j >= 1 && j <= dp.n) dp.out[(size_t)i * (dp.n + 1) + j] = half_of(e_new, 0) + p.sc.G;
     });
