@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SWB_NVCC_EXTRA", "").split()
     jobs = [[nvcc] + CFLAGS + extra + ["-c", os.path.join(CSRC, "swb200.cu"), "-o", os.path.join(OBJ, "swb200.o")]]
     for r in R_SET:
         jobs.append([nvcc] + CFLAGS + extra + [f"-DSWB_R={r}", "-c", os.path.join(CSRC, "sw_inst.cu"), "-o", os.path.join(OBJ, f"sw_inst_r{r}.o")])

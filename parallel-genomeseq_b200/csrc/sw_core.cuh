@@ -437,11 +437,10 @@ struct Wavefront {
   // Pass-2 replay: a plain one-step loop (scores straight from the select, symbols one step ahead).  Pass 2
   // is short and has several replay sites per kernel; the compact body keeps them inside the instruction
   // cache, which matters more there than the software pipelining of the score pass.
-  template <bool BND, class Hook>
-  __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook) {
+  template <bool BND, class Hook, class Post>
+  __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook, Post&& post) {
     restore(pd, t0);
     if (BND) chunk_next = load_chunk(pd, (C * t0) >> 5);  // B >= 32, so C * t0 is a multiple of 32
-    uint32_t bmax = NEG_INF2;
     uint32_t ynext[C], ynext2[C];                          // symbols of the next two steps (loads stay two steps ahead)
     load_symbols_m<true>(pd, t0 + 1, ynext);
     load_symbols_m<true>(pd, t0 + 2, ynext2);
@@ -453,23 +452,30 @@ struct Wavefront {
       load_symbols_m<true>(pd, t + 2, ynext2);
       const bool on = t <= t1;
       auto h = [&](int k, int c, int tt, int j, uint32_t e_new) { if (on) hook(k, c, tt, j, e_new); };
+      uint32_t smax = NEG_INF2;                            // maximum over this step's cells
       if (PROFILE) {
 #pragma unroll
         for (int c = 0; c < C; ++c) psel.set_column(c, ycur[c]);
-        step_sel<BND>(pd, t, psel, bmax, h);
+        step_sel<BND>(pd, t, psel, smax, h);
       } else {
 #pragma unroll
         for (int c = 0; c < C; ++c) csel.set_column(c, ycur[c]);
-        step_sel<BND>(pd, t, csel, bmax, h);
+        step_sel<BND>(pd, t, csel, smax, h);
       }
+      post(t, on, smax);
     }
   }
-  // replay never writes boundary rows or progress counters again, it only reads boundary rows
+  // replay never writes boundary rows or progress counters again, it only reads boundary rows.
+  // hook(k, c, t, j, E_new) fires for every cell of steps <= t1, post(t, on, step_max) after every step.
+  template <class Hook, class Post>
+  __device__ __forceinline__ void replay(const PairDesc& pd, bool multi, int t0, int t1, int nsteps, Hook&& hook, Post&& post) {
+    bnd_out = nullptr; wait_on = nullptr; publish_to = nullptr;
+    if (multi) replay_impl<true>(pd, t0, t1, nsteps, hook, post);
+    else replay_impl<false>(pd, t0, t1, nsteps, hook, post);
+  }
   template <class Hook>
   __device__ __forceinline__ void replay(const PairDesc& pd, bool multi, int t0, int t1, int nsteps, Hook&& hook) {
-    bnd_out = nullptr; wait_on = nullptr; publish_to = nullptr;
-    if (multi) replay_impl<true>(pd, t0, t1, nsteps, hook);
-    else replay_impl<false>(pd, t0, t1, nsteps, hook);
+    replay(pd, multi, t0, t1, nsteps, hook, [](int, bool, uint32_t) {});
   }
 };
 
@@ -630,7 +636,6 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
   const int groups_per_warp = 32 >> p.logL;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const int ggroup = gwarp * groups_per_warp + grp_in_warp;
   // ring of recomputed steps, one per warp: word (((t & (Wc-1)) * C + c) * R + k) * 32 + lane, so the 32 lanes of a
   // store are contiguous and every offset inside a step is a compile-time constant (groups of a warp may sit at
   // different steps t; they write disjoint lanes of different ring rows)
@@ -733,15 +738,28 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       if (multi && us != cur_strip) { cur_strip = us; wf.prepare(pd, us, prof_warp); }
       const int row0 = cur_strip * S + g * R + 1;
       uint64_t mine = ~0ull;
-      wf.replay(pd, multi, t0, has ? t0 + p.B : -1, p.B, [&](int k, int, int, int j, uint32_t e_new) {
-        if (((e_new ^ vmax2) & hmask) == 0) {
-          const int i = row0 + k;
-          if (i <= m && j >= 1 && j <= n) {
-            const uint64_t key = (tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j);
-            mine = key < mine ? key : mine;
-          }
+      auto consider = [&](int i, int j) {
+        if (i <= m && j >= 1 && j <= n) {
+          const uint64_t key = (tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j);
+          mine = key < mine ? key : mine;
         }
-      });
+      };
+      if (C == 1) {
+        // one column per step: the step's cells are still in the lane state afterwards, so a step is examined
+        // only when its maximum reaches vmax (no cell of this half can exceed it)
+        wf.replay(pd, multi, t0, has ? t0 + p.B : -1, p.B, [](int, int, int, int, uint32_t) {}, [&](int t, bool on, uint32_t smax) {
+          if (on && ((smax ^ vmax2) & hmask) == 0) {
+            const int j = col_of<C>(t, g, 0);
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+              if (((wf.st.E[k] ^ vmax2) & hmask) == 0) consider(row0 + k, j);   // unrolled: saturated plateaus hit often
+          }
+        });
+      } else {
+        wf.replay(pd, multi, t0, has ? t0 + p.B : -1, p.B, [&](int k, int, int, int j, uint32_t e_new) {
+          if (((e_new ^ vmax2) & hmask) == 0) consider(row0 + k, j);
+        });
+      }
       mine = group_min_u64(mine, L);
       best = mine < best ? mine : best;
       if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 11, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
@@ -775,12 +793,19 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
     uint8_t* cx = tp.out_cx + (size_t)td.out * tp.cons_cap;
     uint8_t* cy = tp.out_cy + (size_t)td.out * tp.cons_cap;
     bool done = !active;
+    bool first_session = true;
+    const int est_len = 2 * row_min + 16;
     while (!__all_sync(0xffffffffu, done)) {
       const int ss = (ix - 1) / S;                       // strip of row ix
       const int il = ix - ss * S;                        // row within the strip, 1..S
       const int l_e = (il - 1) / R;
       const int t_hi = done ? 0 : step_of<C>(iy, l_e);
-      int c_lo = iy - 2 - (il + 8);      // restart at a checkpoint left of the columns the remaining rows can reach
+      // restart at a checkpoint left of the columns the remaining rows can reach; the first session of a task
+      // looks back only as far as a path of twice the minimum length for its score needs (short local alignments
+      // in tall strips), later sessions the full distance
+      int look = il + 8;
+      if (first_session) look = min(look, est_len);
+      int c_lo = iy - 2 - look;
       if (c_lo < 0) c_lo = 0;
       const int t_lo = done ? 0 : (((c_lo / C) >> p.logB) << p.logB);
       const int valid_lo = max(C * t_lo, C * (t_hi - tp.Wc) + 1);   // oldest column every lane still holds
@@ -876,6 +901,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       __syncwarp();
       if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 13, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
       // broadcast the walker's state to its group
+      first_session = false;
       ix = __shfl_sync(0xffffffffu, ix, (int)gshift); iy = __shfl_sync(0xffffffffu, iy, (int)gshift);
       done = __shfl_sync(0xffffffffu, (int)done, (int)gshift) != 0;
     }
