@@ -520,6 +520,9 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   if (p.units) {
     // pipelined strips: this warp owns ONE strip of one pair.  Producers have lower unit indices than their
     // consumers, and thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
+    // NOTE: the host launches score_units_kernel (below) for this mode; this older in-kernel form is unreachable
+    // from the host but stays, because removing it changes the register allocation of this whole kernel and
+    // with it the schedule of the hot single-strip loop (measured 3-5 % slower; see UnitsWavefront).
     if (gwarp >= p.nunits) return;
     const uint2 u = p.units[gwarp];
     const PairDesc pd = p.pairs[u.x];
@@ -555,6 +558,115 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   } else {
     wf.prepare(pd, 0, prof_warp);
     score_pass<R, C, SAT, PROFILE, false>(wf, p, pd, steps, n_min, live);
+  }
+}
+
+// ======================================================================================================
+// Pipelined strips (few long pairs): one warp per (pair, strip) unit, the strips of a pair run concurrently.
+// A strip reads the boundary row of the strip above as soon as that strip has published it (progress
+// counters), 32 columns per coalesced load.  Producers have lower unit indices than their consumers, and
+// thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
+//
+// This path has a kernel and a stepping routine of its own (UnitsWavefront adds to Wavefront, it changes
+// nothing in it): ptxas allocates registers and schedules per kernel, and the batched kernel above is
+// sensitive to it (A/B on one box: +-3-5 % on the hot loop from unrelated edits to shared code).  Differences
+// to Wavefront::step_sel<true>: the boundary row is stored by a precomputed writer lane without range tests in
+// interior blocks, and progress is published once per few blocks instead of being tested per column.
+// ======================================================================================================
+template <int R, int C, bool SAT, bool PROFILE>
+struct UnitsWavefront : Wavefront<R, C, SAT, PROFILE> {
+  using Base = Wavefront<R, C, SAT, PROFILE>;
+  bool writer = false;     // lane 31 of a strip that has a strip below it
+  __device__ __forceinline__ UnitsWavefront(const PassParams& p_) : Base(p_) {}
+
+  template <bool MASKED, class Sel>
+  __device__ __forceinline__ void step_units(const PairDesc& pd, int t, const Sel& sel, uint32_t& bmax) {
+    uint32_t upv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      upv[c] = __shfl_up_sync(0xffffffffu, this->st.bot[c], 1);
+      const int base = C * (t - 1);                       // 0-based column of lane 0's first column in this step
+      if (c == 0 && (base & 31) == 0) { this->chunk_cur = this->chunk_next; this->chunk_next = this->load_chunk(pd, (base >> 5) + 1); }
+      const uint32_t north = __shfl_sync(0xffffffffu, this->chunk_cur, (base & 31) + c);
+      if (this->lane == 0) upv[c] = north;
+    }
+    step<R, C, SAT>(this->st, sel, this->p.sc, upv, bmax, [](int, int, uint32_t) {});
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = col_of<C>(t, this->lane, c);
+      if (writer && (!MASKED || (j >= 1 && j <= (int)pd.n))) this->bnd_out[j] = this->st.bot[c];
+    }
+  }
+  // steps t and t+1, software-pipelined like Wavefront::two_steps
+  template <bool MASKED>
+  __device__ __forceinline__ void two_steps_units(const PairDesc& pd, int t, uint32_t& bmax) {
+    if (PROFILE) {
+      this->template load_symbols_m<MASKED>(pd, t + 2, this->py1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) this->psel.set_column(c, this->py0[c]);
+      this->rb.fetch(this->psel);
+      step_units<MASKED>(pd, t, this->ra, bmax);
+      this->template load_symbols_m<MASKED>(pd, t + 3, this->py0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) this->psel.set_column(c, this->py1[c]);
+      this->ra.fetch(this->psel);
+      step_units<MASKED>(pd, t + 1, this->rb, bmax);
+    } else {
+      uint32_t y2[C];
+      this->template load_symbols_m<MASKED>(pd, t + 2, y2);
+#pragma unroll
+      for (int c = 0; c < C; ++c) this->csel.set_column(c, this->py0[c]);
+      step_units<MASKED>(pd, t, this->csel, bmax);
+      this->template load_symbols_m<MASKED>(pd, t + 3, this->py0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) this->csel.set_column(c, this->py1[c]);
+      step_units<MASKED>(pd, t + 1, this->csel, bmax);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { const uint32_t tmp = this->py0[c]; this->py0[c] = y2[c]; this->py1[c] = tmp; }
+    }
+  }
+};
+
+template <int R, int C, bool SAT, bool PROFILE>
+__global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
+  extern __shared__ uint32_t smem_prof[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+  if (gwarp >= p.nunits) return;
+  const uint2 u = p.units[gwarp];
+  const PairDesc pd = p.pairs[u.x];
+  UnitsWavefront<R, C, SAT, PROFILE> wf(p);
+  wf.L = 32; wf.g = lane; wf.lane = lane;
+  wf.prepare(pd, (int)u.y, prof_warp);
+  wf.writer = wf.bnd_out != nullptr && lane == 31;
+  wf.wait_on = u.y > 0 ? p.progress + (gwarp - 1) : nullptr;
+  uint32_t* const publish_to = (u.y + 1 < pd.nstrips) ? p.progress + gwarp : nullptr;   // wf.publish_to stays null: no per-column publishing
+
+  uint32_t* blk = p.blkmax + pd.blk_off;
+  uint32_t* ck = p.ckpt + pd.ck_off;
+  const int n = (int)pd.n;
+  const int nb = (int)pd.nblk;
+  // publishing costs a fence, waiting for it costs pipeline lag down the chain of strips: balance the two
+  const int pub_every = max(1, min(16, (int)sqrtf(0.1f * (float)nb / (float)max(1u, pd.nstrips))));
+  int since_pub = 0;
+  wf.template begin<true>(pd, 0);
+  uint32_t bmax = NEG_INF2;
+  for (int b = 0; b < nb; ++b) {
+    const int t0 = b << p.logB;
+    const bool interior = (t0 + 1 >= 32) && ((t0 + p.B + 2) * C <= n);
+    if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<false>(pd, t, bmax); }
+    else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<true>(pd, t, bmax); }
+    const uint32_t gm = group_max_s16x2(bmax, 32);
+    if (lane == 0) blk[wf.blk_index(pd, b)] = gm;
+    save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), 32, lane);
+    bmax = NEG_INF2;
+    if (publish_to && (++since_pub >= pub_every || b == nb - 1)) {
+      since_pub = 0;
+      const int jd = min(n, col_of<C>(t0 + p.B, 31, C - 1));    // last column lane 31 has finished
+      if (lane == 31 && jd >= 1) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)jd; }
+    }
   }
 }
 

@@ -26,6 +26,11 @@ cudaError_t score_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, 
   return sat ? go(score_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(score_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
 }
 template <int C>
+cudaError_t score_units_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  if (profile) return sat ? go(score_units_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(score_units_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
+  return sat ? go(score_units_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(score_units_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
+}
+template <int C>
 cudaError_t trace_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
   if (profile) return sat ? go(trace_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
   return sat ? go(trace_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(trace_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
@@ -41,6 +46,7 @@ cudaError_t SWB_CAT(swb_launch_dump_r, SWB_R)(bool sat, bool profile, size_t sme
   return dump_c<1>(sat, profile, smem, st, p);
 }
 cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  if (p.units) return C == 1 ? score_units_c<1>(sat, profile, grid, block, smem, st, p) : score_units_c<2>(sat, profile, grid, block, smem, st, p);
   return C == 1 ? score_c<1>(sat, profile, grid, block, smem, st, p) : score_c<2>(sat, profile, grid, block, smem, st, p);
 }
 cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
