@@ -933,9 +933,12 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       const int nsteps = warp_max_i32(t_hi - t_lo);
       if (tp.counters) { if (!done && g == 0) atomicAdd(tp.counters + 1, 1ull); if (lane == 0) { atomicAdd(tp.counters + 3, 1ull); atomicAdd(tp.counters + 4, (unsigned long long)nsteps); } }
       uint32_t* const scr_lane = scr + lane;
-      wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int c, int t, int j, uint32_t e_new) {
-        // lane g computes column j in step t = g + ceil(j / C); virtual columns j <= 0 hold H = 0 and are never read
-        if (j >= 1) (scr_lane + (uint32_t)(t & wmask) * RING_STEP)[(c * R + k) * 32] = e_new;
+      // Lane g computes column j in step t = g + ceil(j / C): j >= 1 <=> t >= g + 1 (virtual columns j <= 0 hold
+      // H = 0 and are never read).  Only the last Wc steps of the session survive in the ring, so the steps
+      // before them (a session starts at a checkpoint, up to B steps early) are replayed without storing.
+      const int t_store = max(g + 1, t_hi - tp.Wc + 1);
+      wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int c, int t, int, uint32_t e_new) {
+        if (t >= t_store) (scr_lane + (uint32_t)(t & wmask) * RING_STEP)[(c * R + k) * 32] = e_new;
       });
       __syncwarp();
       if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 12, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }

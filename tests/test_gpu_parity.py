@@ -213,6 +213,26 @@ def test_long_pair_c5_shape(engine, pkg):
             _check(r, i, o.align(x, ref, mode=omode), tag=("c5", mode))
 
 
+def test_pipelined_strips_sparse_publishing(engine, pkg):
+    """Few long pairs against a long reference: the strips of a pair run concurrently (score_units_kernel) and a
+    strip publishes its progress only every few checkpoint blocks (interval > 1 needs many blocks per strip,
+    which the 30 kbp case above does not have).  Oracle parity, both modes, incl. a read without a good match."""
+    ref = synth.c3_reference(120_000, seed=41)
+    reads = synth.mutated_reads(ref, 2, 1_400, seed=42, sub=0.03, ins=0.003, dele=0.003)
+    rng = np.random.default_rng(43)
+    reads.append("".join(rng.choice(list("ACGT"), size=1_150)))
+    for mode, omode in ((pkg.MODE_EXACT, o.MODE_EXACT), (pkg.MODE_SAT_U8, o.MODE_SAT_U8)):
+        engine.set_scoring_match(mode, 3, -3, 2)
+        engine.set_reference(ref)
+        r = engine.align(reads, cons_stride=4_000)
+        st = engine.stats()
+        assert st["lanes_per_pair"] == 32 and st["rows_per_lane"] * 32 < 1_150, st   # really cut into strips
+        for i, x in enumerate(reads):
+            w = o.align(x, ref, mode=omode)
+            _check(r, i, w, tag=("units", mode, len(x)))
+            assert tuple(r["end"][i]) == w["end"]
+
+
 def test_dense_matrix_accessor(engine, pkg):
     """operator()(row, col) surface: every cell of H through the device path equals the oracle
     (test/test_skewedmatrix.cpp:39-66 compares the two SMTs cell by cell; test_localaligner.cpp:31-42 golden H)."""
