@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libswb200.so")
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 R_SET = [2, 4, 5, 8, 12, 16, 19, 24, 32]   # must match kRSet / SWB_DECL in csrc/swb200.cu
-DEPS = [os.path.join(CSRC, f) for f in ("swb200.cu", "sw_inst.cu", "sw_core.cuh")] + [os.path.join(os.path.dirname(HERE), "include", "swb200.h")]
+DEPS = [os.path.join(CSRC, f) for f in ("swb200.cu", "sw_inst.cu", "sw_core.cuh", "sw_qs.cuh")] + [os.path.join(os.path.dirname(HERE), "include", "swb200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

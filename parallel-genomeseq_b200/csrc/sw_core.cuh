@@ -733,12 +733,14 @@ __device__ __forceinline__ int group_max_i32(int v, int L) {
   return v;
 }
 
-template <int R, int C, bool SAT, bool PROFILE>
+// QS = query-stationary frame (sw_qs.cuh): the kernel's rows are the reference's y (the shared query, qs_m rows)
+// and its columns the reference's x (a database sequence per half); WF is then QsWavefront and the arg-max order
+// and the traceback priority are expressed in that transposed frame.
 #ifndef SWB_TRACE_MINBLOCKS
 #define SWB_TRACE_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const TraceParams tp) {
-  extern __shared__ uint32_t smem_prof[];
+template <int R, int C, bool SAT, bool PROFILE, bool QS, class WF>
+__device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem_prof, int qs_m) {
   const PassParams& p = tp.pp;
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -758,9 +760,9 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
   const int S = L * R;                 // rows per strip
   const uint32_t gshift = (uint32_t)(grp_in_warp * L);
   const uint32_t gbits = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
-  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+  uint32_t* prof_warp = QS ? smem_prof : smem_prof + (size_t)warp_in_cta * p.KP * R * 32;   // QS: one profile per CTA
 
-  Wavefront<R, C, SAT, PROFILE> wf(p);
+  WF wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
 
   for (int base = gwarp * groups_per_warp; base < tp.ntasks; base += nwarps * groups_per_warp) {   // warp-uniform
@@ -768,14 +770,15 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
     bool active = ti < tp.ntasks;
     const TaskDesc td = tp.tasks[tp.task_list ? tp.task_list[active ? ti : base] : (active ? ti : base)];
     const PairDesc pd = p.pairs[td.pair];
-    const int m = td.half ? pd.mB : pd.mA;
-    const int n = pd.n;
+    const int m = QS ? qs_m : (int)(td.half ? pd.mB : pd.mA);     // rows of the kernel frame
+    const int n = QS ? (int)(td.half ? pd.mB : pd.mA) : (int)pd.n; // columns of the kernel frame
     const int nblk = (int)pd.nblk;
     const int nunits = nblk * (int)pd.nstrips;       // (strip, block) units
     const bool multi = warp_max_i32((int)pd.nstrips) > 1;   // > 1 only with L == 32: one group per warp
     const uint32_t half = td.half;
-    const uint8_t* xraw = p.reads_raw + (td.half ? pd.xB : pd.xA);
-    const uint8_t* yraw = p.ref_raw + pd.y_off;
+    // characters along the kernel's rows / columns (QS: rows = the query in reads_raw, columns = a database sequence)
+    const uint8_t* xraw = QS ? p.reads_raw : p.reads_raw + (td.half ? pd.xB : pd.xA);
+    const uint8_t* yraw = QS ? p.ref_raw + (td.half ? pd.xB : pd.xA) : p.ref_raw + pd.y_off;
     long long tk0 = clock64();
     int cur_strip = 0;
     wf.prepare(pd, 0, prof_warp);
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
               uint64_t lb;
               // smallest raw column of the unit: d_min for ordinary cells, d_min - ncols (>= 0) for wrapped ones
               if (tp.mode == MODE_SAT_U8) lb = (uint64_t)(uint32_t)(wraps ? max(0, jmin + imin - ncols_raw) : jmin + imin) << 32;
-              else lb = (uint64_t)(uint32_t)jmin << 32;
+              else lb = (uint64_t)(uint32_t)(QS ? imin : jmin) << 32;
               cand = (lb <= best) && (wraps == (phase == 0));
             }
           }
@@ -852,7 +855,8 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       uint64_t mine = ~0ull;
       auto consider = [&](int i, int j) {
         if (i <= m && j >= 1 && j <= n) {
-          const uint64_t key = (tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j);
+          const uint64_t key = QS ? ((tp.mode == MODE_SAT_U8) ? skew_key(j, i, n, m) : colmajor_key(j, i))
+                                  : ((tp.mode == MODE_SAT_U8) ? skew_key(i, j, m, n) : colmajor_key(i, j));
           mine = key < mine ? key : mine;
         }
       };
@@ -881,18 +885,19 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       if (tp.mode == MODE_SAT_U8) {
         // invert skew_key: _rawindex2trueindex, similaritymatrix.cpp:330-346
         const int rj = (int)(best >> 32), ri = (int)(uint32_t)best;
-        const int len_x = n + 1, len_y = m + 1, nrows = min(len_x, len_y);
+        const int len_x = (QS ? m : n) + 1, len_y = (QS ? n : m) + 1, nrows = min(len_x, len_y);
         int t_i, t_j;
         if (rj < nrows - 1) {
           if (ri <= rj) { t_i = ri; t_j = rj - ri; } else { t_i = len_x - nrows + ri; t_j = len_y - ri + rj; }
         } else {
           if (len_x <= len_y) { t_i = ri; t_j = rj - ri; } else { t_i = rj - (nrows - 1) + ri; t_j = nrows - 1 - ri; }
         }
-        je = t_i; ie = t_j;
-      } else { je = (int)(best >> 32); ie = (int)(uint32_t)best; }
+        if (QS) { ie = t_i; je = t_j; } else { je = t_i; ie = t_j; }
+      } else if (QS) { ie = (int)(best >> 32); je = (int)(uint32_t)best; }
+      else { je = (int)(best >> 32); ie = (int)(uint32_t)best; }
       if (g == 0) {
         tp.out_score[td.out] = score;
-        tp.out_end[2 * td.out] = (uint32_t)ie; tp.out_end[2 * td.out + 1] = (uint32_t)je;
+        tp.out_end[2 * td.out] = (uint32_t)(QS ? je : ie); tp.out_end[2 * td.out + 1] = (uint32_t)(QS ? ie : je);
       }
     }
 
@@ -975,8 +980,10 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
               const int cx_ = ix - d, cy_ = iy - d;
               okd[d] = d == 0 || (cx_ > row_lo && (cy_ - 1 >= valid_lo || cy_ - 1 <= 0) && cy_ >= 1);
               q1[d] = okd[d] ? cell_ptr(cx_ - 1, cy_ - 1) : nullptr;
-              q2[d] = okd[d] ? cell_ptr(cx_, cy_ - 1) : nullptr;
-              q3[d] = okd[d] ? cell_ptr(cx_ - 1, cy_) : nullptr;
+              // the reference's second neighbour is H(ix, iy-1) and its third H(ix-1, iy); in the QS frame those
+              // are the cell above and the cell to the left
+              q2[d] = okd[d] ? (QS ? cell_ptr(cx_ - 1, cy_) : cell_ptr(cx_, cy_ - 1)) : nullptr;
+              q3[d] = okd[d] ? (QS ? cell_ptr(cx_, cy_ - 1) : cell_ptr(cx_ - 1, cy_)) : nullptr;
             }
             uint32_t w1[SPEC], w2[SPEC], w3[SPEC];
 #pragma unroll
@@ -998,13 +1005,14 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
           for (int d = 0; d < SPEC; ++d) if (d == at) { n1 = v1[d]; n2 = v2[d]; n3 = v3[d]; xc = xb[d]; yc = yb[d]; }
           if (n1 < 0) { have = 0; continue; }                // speculation ran out of the safe region: reload here
           if (len >= tp.cons_cap) { flags |= 1u; done = true; break; }
+          const uint8_t rx = QS ? yc : xc, ry = QS ? xc : yc;   // the reference's x / y characters of this cell
           if (n1 == 0 || n2 == 0 || n3 == 0) {
-            if (tp.want_consensus) { cx[len] = xc; cy[len] = yc; }
-            ++len; pos = (uint32_t)iy; done = true; break;
+            if (tp.want_consensus) { cx[len] = rx; cy[len] = ry; }
+            ++len; pos = (uint32_t)(QS ? ix : iy); done = true; break;
           }
-          if (n1 >= n2 && n1 >= n3) { if (tp.want_consensus) { cx[len] = xc; cy[len] = yc; } --ix; --iy; ++at; }
-          else if (n2 >= n1 && n2 >= n3) { if (tp.want_consensus) { cx[len] = '-'; cy[len] = yc; } --iy; have = 0; }
-          else { if (tp.want_consensus) { cx[len] = xc; cy[len] = '-'; } --ix; have = 0; }
+          if (n1 >= n2 && n1 >= n3) { if (tp.want_consensus) { cx[len] = rx; cy[len] = ry; } --ix; --iy; ++at; }
+          else if (n2 >= n1 && n2 >= n3) { if (tp.want_consensus) { cx[len] = '-'; cy[len] = ry; } if (QS) --ix; else --iy; have = 0; }
+          else { if (tp.want_consensus) { cx[len] = rx; cy[len] = '-'; } if (QS) --iy; else --ix; have = 0; }
           ++len;
         }
         if (done) {
@@ -1021,6 +1029,12 @@ __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const T
       done = __shfl_sync(0xffffffffu, (int)done, (int)gshift) != 0;
     }
   }
+}
+
+template <int R, int C, bool SAT, bool PROFILE>
+__global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const TraceParams tp) {
+  extern __shared__ uint32_t smem_prof[];
+  trace_body<R, C, SAT, PROFILE, false, Wavefront<R, C, SAT, PROFILE>>(tp, smem_prof, 0);
 }
 
 // ======================================================================================================

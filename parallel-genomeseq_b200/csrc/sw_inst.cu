@@ -1,6 +1,7 @@
 // sw_inst.cu — explicit instantiation of the wavefront kernels for ONE rows-per-lane value (-DSWB_R=<R>).
 // build.py compiles this file once per R in parallel and links the objects into libswb200.so.
 #include "sw_core.cuh"
+#include "sw_qs.cuh"
 
 #ifndef SWB_R
 #error "compile with -DSWB_R=<rows per lane>"
@@ -51,4 +52,12 @@ cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, bool sat, bool profile, di
 }
 cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
   return C == 1 ? trace_c<1>(sat, profile, grid, block, smem, st, p) : trace_c<2>(sat, profile, grid, block, smem, st, p);
+}
+
+// query-stationary kernels (sw_qs.cuh): one column per step, profile select
+cudaError_t SWB_CAT(swb_launch_qs_score_r, SWB_R)(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsParams& p) {
+  return sat ? go(qs_score_kernel<SWB_R, true>, grid, block, smem, st, p) : go(qs_score_kernel<SWB_R, false>, grid, block, smem, st, p);
+}
+cudaError_t SWB_CAT(swb_launch_qs_trace_r, SWB_R)(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsTraceParams& p) {
+  return sat ? go(qs_trace_kernel<SWB_R, true>, grid, block, smem, st, p) : go(qs_trace_kernel<SWB_R, false>, grid, block, smem, st, p);
 }

@@ -23,6 +23,7 @@
 
 #define SWB_HELPER_KERNELS 1
 #include "sw_core.cuh"
+#include "sw_qs.cuh"
 
 using namespace swb;
 
@@ -30,7 +31,9 @@ using namespace swb;
 #define SWB_DECL(RR)                                                                                                  \
   cudaError_t swb_launch_score_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p); \
   cudaError_t swb_launch_trace_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p); \
-  cudaError_t swb_launch_dump_r##RR(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p);
+  cudaError_t swb_launch_dump_r##RR(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p);       \
+  cudaError_t swb_launch_qs_score_r##RR(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsParams& p); \
+  cudaError_t swb_launch_qs_trace_r##RR(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsTraceParams& p);
 SWB_DECL(2) SWB_DECL(4) SWB_DECL(5) SWB_DECL(8) SWB_DECL(12) SWB_DECL(16) SWB_DECL(19) SWB_DECL(24) SWB_DECL(32)
 #undef SWB_DECL
 
@@ -104,6 +107,10 @@ struct swb_ctx {
   std::vector<LaunchClass> classes;
   DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
+  // query-stationary mode (sw_qs.cuh): database search against a short reference, computed transposed
+  bool qs = false;
+  int qs_KP = 0;
+  DevBuf d_xcode, d_qs_table;
   swb_stats stats{};
   std::vector<cudaEvent_t> ev_pool;   // event pairs around every pass-2 launch of the current run
   size_t ev_used = 0;
@@ -220,6 +227,22 @@ cudaError_t launch_trace(int R, int C, bool sat, bool profile, dim3 grid, dim3 b
   }
 }
 
+cudaError_t launch_qs_score(int R, bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsParams& p) {
+  switch (R) {
+#define SWB_CASE(RR) case RR: return swb_launch_qs_score_r##RR(sat, grid, block, smem, st, p);
+    SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
+#undef SWB_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+cudaError_t launch_qs_trace(int R, bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsTraceParams& p) {
+  switch (R) {
+#define SWB_CASE(RR) case RR: return swb_launch_qs_trace_r##RR(sat, grid, block, smem, st, p);
+    SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
+#undef SWB_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
 cudaError_t launch_dump(int R, bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
   switch (R) {
 #define SWB_CASE(RR) case RR: return swb_launch_dump_r##RR(sat, profile, smem, st, p);
@@ -584,6 +607,216 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
   return SWB_OK;
 }
 
+
+// ---- query-stationary mode (sw_qs.cuh) -----------------------------------------------------------------------
+// Database search: many sequences against ONE short reference (mpi_sw_solve_uniprot.cpp: x = database protein,
+// y = query).  The matrix is computed transposed (rows = y, shared by every alignment; columns = x), see sw_qs.cuh.
+// Used when the scoring is tabulated (a substitution matrix), the batch is large and y fits one strip;
+// SWB_QSTAT=0 / 1 forces it off / on (where applicable).  Returns 1 when the mode does not apply (caller falls back).
+int stage_qs(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_seqs, unsigned flags) {
+  const HostScoring& hs = ctx->sc;
+  const size_t N = ctx->y.size();
+  const char* env = getenv("SWB_QSTAT");
+  if (env && atoi(env) == 0) return 1;
+  const bool forced = env && atoi(env) != 0;
+  if (!forced && (hs.match_shaped || n_seqs < 2048 || N > 608)) return 1;
+  if (ctx->force_l32 || N > 1024) return 1;
+  // geometry: L*R >= N rows with the least padding (ties: fewer lanes, i.e. more pairs per warp)
+  Geometry geo;
+  size_t best_rows = ~(size_t)0;
+  for (int L = 8; L <= 32; L <<= 1)
+    for (int i = 0; i < kNumR; ++i)
+      if ((size_t)L * kRSet[i] >= N) { if ((size_t)L * kRSet[i] < best_rows) { best_rows = (size_t)L * kRSet[i]; geo.L = L; geo.logL = ilog2(L); geo.R = kRSet[i]; } break; }
+  if (!geo.L) return 1;
+  const int L = geo.L, R = geo.R;
+  // alphabet of the batch (the kernel's column symbols)
+  const size_t blob = offsets[n_seqs] - offsets[0];
+  uint8_t xcode_of[256]; memset(xcode_of, 0xFF, sizeof xcode_of);
+  uint8_t byte_of[256]; memset(byte_of, 0, sizeof byte_of);
+  int KX = 0;
+  std::vector<uint8_t> codes(blob);
+  const uint8_t* src = (const uint8_t*)seqs + offsets[0];
+  for (size_t i = 0; i < blob; ++i) {
+    const uint8_t b = src[i];
+    if (xcode_of[b] == 0xFF) { if (KX >= 254) return 1; byte_of[KX] = b; xcode_of[b] = (uint8_t)KX++; }
+    codes[i] = xcode_of[b];
+  }
+  const int KP = KX + 1;
+  if ((size_t)KP * R * 128 > 200 * 1024) return 1;      // one profile per thread block
+  uint32_t max_m = 0;
+  uint64_t cells_ref = 0;
+  for (size_t r = 0; r < n_seqs; ++r) {
+    const uint64_t m64 = offsets[r + 1] - offsets[r];
+    if (m64 == 0) return fail(ctx, SWB_ERR_ARG, "empty sequence at index " + std::to_string(r));
+    max_m = std::max(max_m, (uint32_t)m64);
+    cells_ref += m64 * N;
+  }
+  {
+    const uint64_t reach = (uint64_t)std::min<size_t>(max_m, N) * (uint64_t)std::max(1, hs.max_pos) + (uint64_t)hs.G + 16;
+    if (hs.mode == SWB_MODE_EXACT && reach > 32000)
+      return fail(ctx, SWB_ERR_UNSUPPORTED, "EXACT-mode scores may exceed the 16-bit lane range (min(len) * max score = " + std::to_string(reach) + "); the 32-bit path is not built yet");
+  }
+  ctx->C = 1;
+  // (s + G) table: rows = reference (query) byte, 256 = padding row; columns = batch code, KP-1 = padding column
+  std::vector<int16_t> t((size_t)257 * KP, (int16_t)(-16000));
+  for (int a = 0; a < 256; ++a)
+    for (int c = 0; c < KP - 1; ++c) {
+      const int xb = byte_of[c];
+      const int sc = hs.match_shaped ? (xb == a ? hs.M : -hs.X) : hs.table[(size_t)xb * 256 + a];
+      t[(size_t)a * KP + c] = (int16_t)(sc + hs.G);
+    }
+  // sequences by decreasing length: pair-mates of similar length, long ones scheduled first
+  std::vector<uint32_t> order(n_seqs);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return offsets[a + 1] - offsets[a] > offsets[b + 1] - offsets[b]; });
+  const size_t ckw = hs.mode == SWB_MODE_SAT_U8 ? (size_t)(R + 2) / 2 : (size_t)(R + 1);     // state_words<R, 1, SAT>
+  size_t budget_mb = 8192;
+  if (const char* e = getenv("SWB_CKPT_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
+  const size_t chunk_tasks = 2 * chunk_pairs(ctx);
+  int B = 16;       // short checkpoint period: pass 2 replays O(B) columns per scan and per session
+  if (const char* e = getenv("SWB_QS_B")) B = std::max(8, std::min(1024, 1 << ilog2(atoi(e))));
+  for (;; B <<= 1) {
+    size_t worst = 0;
+    for (size_t o = 0; o < n_seqs; o += chunk_tasks) {
+      size_t words = 0;
+      for (size_t k = o; k < std::min(n_seqs, o + chunk_tasks); k += 2) {
+        const size_t n = offsets[order[k] + 1] - offsets[order[k]];
+        words += ((n + L - 1 + B - 1) / B) * ckw * L;
+      }
+      worst = std::max(worst, words);
+    }
+    if (worst * 4 <= budget_mb * 1048576 || B >= 65536) break;
+  }
+  ctx->B = B; ctx->logB = ilog2(B);
+  free_classes(ctx->classes);
+  for (size_t o = 0; o < n_seqs; o += chunk_tasks) {
+    ctx->classes.emplace_back();
+    LaunchClass& lc = ctx->classes.back();
+    lc.geo = geo; lc.pieces = 1; lc.max_m = (int)N; lc.max_strips = 1;
+    const size_t end = std::min(n_seqs, o + chunk_tasks);
+    lc.nreads = (int)(end - o);
+    for (size_t k = o; k < end; k += 2) {
+      const uint32_t ra = order[k];
+      PairDesc pd{};
+      pd.mA = (uint32_t)(offsets[ra + 1] - offsets[ra]); pd.xA = (uint32_t)(offsets[ra] - offsets[0]);
+      const uint32_t pair_idx = (uint32_t)lc.pairs.size();
+      lc.tasks.push_back(TaskDesc{pair_idx, 0u, ra, 0u});
+      if (k + 1 < end) {
+        const uint32_t rb = order[k + 1];
+        pd.mB = (uint32_t)(offsets[rb + 1] - offsets[rb]); pd.xB = (uint32_t)(offsets[rb] - offsets[0]);
+        lc.tasks.push_back(TaskDesc{pair_idx, 1u, rb, 0u});
+      } else { pd.mB = 0; pd.xB = pd.xA; }
+      pd.y_off = 0; pd.n = std::max(pd.mA, pd.mB);
+      pd.nblk = (uint32_t)((pd.n + L - 1 + B - 1) / B);
+      pd.nstrips = 1;
+      pd.blk_off = lc.blk_words; lc.blk_words += pd.nblk;
+      pd.ck_off = lc.ck_words; lc.ck_words += (size_t)pd.nblk * ckw * L;
+      lc.pairs.push_back(pd);
+    }
+  }
+  CUDA_TRY(ctx->d_reads.ensure(blob + 64));
+  CUDA_TRY(ctx->d_xcode.ensure(blob + 64));
+  CUDA_TRY(ctx->d_qs_table.ensure(t.size() * sizeof(int16_t)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_reads.p, src, blob, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_xcode.p, codes.data(), blob, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_qs_table.p, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = upload_classes(ctx, ctx->classes);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));          // codes / t are host temporaries
+  ctx->qs = true; ctx->qs_KP = KP;
+  ctx->stats = swb_stats{};
+  ctx->stats.cells_reference = cells_ref;
+  return SWB_OK;
+}
+
+int run_qs(swb_ctx* ctx) {
+  const HostScoring& hs = ctx->sc;
+  const bool sat = hs.mode == SWB_MODE_SAT_U8;
+  DebugTimer dbg(ctx->stream);
+  for (auto& lc : ctx->classes) {
+    const int L = lc.geo.L, R = lc.geo.R;
+    const int groups_per_warp = 32 / L;
+    CUDA_TRY(ctx->d_blkmax.ensure(lc.blk_words * 4));
+    CUDA_TRY(ctx->d_ckpt.ensure(lc.ck_words * 4));
+    QsParams qp{};
+    PassParams& pp = qp.pp;
+    pp.ref_raw = ctx->d_reads.as<uint8_t>();             // the kernel's columns: the batch
+    pp.ref_code = ctx->d_xcode.as<uint8_t>();
+    pp.reads_raw = ctx->d_ref_raw.as<uint8_t>();         // the kernel's rows: the reference (query)
+    pp.table = ctx->d_qs_table.as<int16_t>();
+    pp.KP = ctx->qs_KP;
+    pp.pairs = lc.d_pairs.as<PairDesc>();
+    pp.npairs = (int)lc.pairs.size();
+    pp.blkmax = ctx->d_blkmax.as<uint32_t>();
+    pp.ckpt = ctx->d_ckpt.as<uint32_t>();
+    pp.L = L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
+    pp.sc = device_scoring(hs, false);
+    pp.sc.G = hs.G;
+    qp.m = (int)ctx->y.size();
+    const size_t smem = (size_t)ctx->qs_KP * R * 32 * 4;      // score pass: 32-bit profile, one per thread block
+    const size_t smem_trace = smem / 2;                       // pass 2: 16-bit profile
+    const int warps_per_cta = 4;
+    {
+      const size_t warps = (lc.pairs.size() + groups_per_warp - 1) / groups_per_warp;
+      const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
+      CUDA_TRY(launch_qs_score(R, sat, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, qp));
+      ctx->stats.kernel_launches++;
+      dbg.mark("qs score", L, R, lc.pairs.size());
+      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nblk * ctx->B * L * R * 2ull;
+    }
+    QsTraceParams qt{};
+    TraceParams& tp = qt.tp;
+    qt.m = qp.m;
+    tp.pp = pp;
+    tp.tasks = lc.d_tasks.as<TaskDesc>();
+    tp.task_list = nullptr;
+    tp.ntasks = (int)lc.tasks.size();
+    tp.mode = hs.mode;
+    tp.max_pos = std::max(1, hs.max_pos);
+    int wc = 64; while (wc < L * R + L + 24) wc <<= 1;
+    tp.Wc = wc; tp.rstride = R * L;
+    const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(uint32_t);
+    size_t max_groups = (size_t)148 * 16 * groups_per_warp;
+    max_groups = std::min(max_groups, std::max<size_t>(groups_per_warp, ((size_t)4 << 30) / per_group));
+    const size_t groups = std::min<size_t>(lc.tasks.size(), max_groups);
+    const size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
+    const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
+    CUDA_TRY(ctx->d_scratch.ensure((size_t)grid * warps_per_cta * groups_per_warp * per_group));
+    tp.scratch = ctx->d_scratch.as<uint32_t>();
+    tp.out_score = ctx->d_score.as<int32_t>();
+    tp.out_pos = ctx->d_pos.as<uint32_t>();
+    tp.out_end = ctx->d_end.as<uint32_t>();
+    tp.out_cx = ctx->d_cx.as<uint8_t>();
+    tp.out_cy = ctx->d_cy.as<uint8_t>();
+    tp.out_len = ctx->d_len.as<uint32_t>();
+    tp.out_flags = ctx->d_flags.as<uint32_t>();
+    tp.cons_cap = (uint32_t)ctx->cons_stride;
+    tp.want_consensus = (ctx->flags & SWB_FLAG_CONSENSUS) ? 1 : 0;
+    if (!tp.want_consensus) tp.cons_cap = 0x7FFFFFFFu;
+    DevBuf d_cnt;
+    tp.counters = nullptr;
+    tp.dbg_flags = 0;
+    if (dbg.on) { CUDA_TRY(d_cnt.ensure(128)); CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 128, ctx->stream)); tp.counters = d_cnt.as<unsigned long long>(); }
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
+    CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    CUDA_TRY(launch_qs_trace(R, sat, dim3(grid), dim3(32 * warps_per_cta), smem_trace, ctx->stream, qt));
+    CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+    ctx->ev_used += 2;
+    ctx->stats.kernel_launches++;
+    dbg.mark("qs trace", L, R, lc.tasks.size());
+    if (dbg.on) {
+      unsigned long long c[16] = {0};
+      cudaMemcpy(c, d_cnt.p, sizeof c, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[swb200]   scan replays %llu, sessions %llu, scan rounds (warps) %llu, session rounds (warps) %llu, session steps %llu\n", c[0], c[1], c[2], c[3], c[4]);
+      fprintf(stderr, "[swb200]   warp-cycles (M): prepare %.1f vmax %.1f search %.1f scan %.1f session %.1f walk %.1f\n", c[8] / 1e6, c[9] / 1e6, c[10] / 1e6, c[11] / 1e6, c[12] / 1e6, c[13] / 1e6);
+      d_cnt.release();
+    }
+    ctx->stats.cells_pass2 += (uint64_t)lc.tasks.size() * (uint64_t)(3 * ctx->B + lc.max_m + 16) * L * R * 2ull;
+    ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
+  }
+  return SWB_OK;
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -612,7 +845,7 @@ void swb_destroy(swb_ctx* ctx) {
   free_classes(ctx->classes);
   for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd, &ctx->d_units, &ctx->d_progress,
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
-                    &ctx->d_len, &ctx->d_flags}) b->release();
+                    &ctx->d_len, &ctx->d_flags, &ctx->d_xcode, &ctx->d_qs_table}) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -727,6 +960,25 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
 
   ctx->n_seqs = n_seqs; ctx->npiece = npiece; ctx->ratio = ratio; ctx->flags = flags; ctx->cons_stride = cons_stride;
   const bool chunked = npiece >= 1;
+  ctx->qs = false;
+  if (!chunked) {
+    const int qrc = stage_qs(ctx, seqs, offsets, n_seqs, flags);
+    if (qrc < 0) return qrc;
+    if (qrc == 0) {
+      CUDA_TRY(ctx->d_score.ensure(n_seqs * 4));
+      CUDA_TRY(ctx->d_pos.ensure(n_seqs * 4));
+      CUDA_TRY(ctx->d_end.ensure(n_seqs * 8));
+      CUDA_TRY(ctx->d_len.ensure(n_seqs * 4));
+      CUDA_TRY(ctx->d_flags.ensure(n_seqs * 4));
+      if (flags & SWB_FLAG_CONSENSUS) {
+        CUDA_TRY(ctx->d_cx.ensure(n_seqs * cons_stride));
+        CUDA_TRY(ctx->d_cy.ensure(n_seqs * cons_stride));
+      }
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      ctx->staged = true;
+      return SWB_OK;
+    }
+  }
 
   // tasks
   const int pieces = chunked ? npiece : 1;
@@ -818,7 +1070,10 @@ int swb_batch_run(swb_ctx* ctx, float* device_us) {
   const bool realign = chunked && !ctx->sc.is_default();
   CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
   ctx->ev_used = 0;
-  if (!realign) {
+  if (ctx->qs) {
+    int rc = run_qs(ctx);
+    if (rc) return rc;
+  } else if (!realign) {
     int rc = run_classes(ctx, ctx->classes.data(), ctx->classes.size(), false, chunked, true);
     if (rc) return rc;
   } else {
