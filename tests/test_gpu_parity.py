@@ -439,3 +439,50 @@ def test_randomised_fuzz_against_oracle():
     env = {k: v for k, v in os.environ.items() if not k.startswith("SWB_")}
     r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "200", "777"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_randomised_fuzz_query_stationary():
+    """The same fuzzer with the query-stationary kernels forced on wherever they apply (unchunked, reference of at
+    most 1024 symbols): random and asymmetric tables, both modes, zero gaps, ragged batches, against the oracle."""
+    import os
+    import subprocess
+    import sys as _sys
+    from conftest import ROOT
+    env = {k: v for k, v in os.environ.items() if not k.startswith("SWB_")}
+    env["SWB_QSTAT"] = "1"
+    r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "300", "2024"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_query_stationary_database_search(engine, pkg, c4_sample, monkeypatch):
+    """BASELINE config 4 through the query-stationary kernels (sw_qs.cuh): the golden C4 sample (forced on: it has
+    fewer sequences than the automatic threshold), then a database large enough to switch the mode on by itself
+    (BLOSUM62 and an asymmetric table), checked against the oracle incl. the arg-max cell."""
+    monkeypatch.setenv("SWB_QSTAT", "1")
+    engine.set_scoring_table(pkg.MODE_EXACT, synth.blosum62_table(), c4_sample["gap"])
+    engine.set_reference(c4_sample["query"])
+    ents = c4_sample["entries"]
+    r = engine.align([e["x"] for e in ents], cons_stride=6000)
+    st = engine.stats()
+    assert (st["lanes_per_pair"], st["rows_per_lane"], st["kernel_launches"]) == (16, 19, 2), st   # one score + one trace launch
+    for i, e in enumerate(ents):
+        _check(r, i, e, tag="c4-qs")
+    monkeypatch.delenv("SWB_QSTAT")
+    rng = np.random.default_rng(77)
+    query = synth.c4_queries(1, 130, seed=5)[0]
+    db = synth.c4_database(2500, seed=6)
+    asym = rng.integers(-5, 4, size=(256, 256)).astype(np.int32)
+    np.fill_diagonal(asym, rng.integers(2, 10, size=256))
+    for table, gap in ((synth.blosum62_table(), 10), (asym, 3)):
+        engine.set_scoring_table(pkg.MODE_EXACT, table, gap)
+        engine.set_reference(query)
+        r = engine.align(db, cons_stride=3000)
+        st = engine.stats()
+        assert st["lanes_per_pair"] * st["rows_per_lane"] >= len(query) and st["kernel_launches"] == 2, st   # automatic
+        for i in range(0, len(db), 9):
+            w = o.align(db[i], query, mode=o.MODE_EXACT, table=table, gap=gap)
+            if w["score"] == 0:
+                assert int(r["score"][i]) == 0 and int(r["len"][i]) == 0
+                continue
+            _check(r, i, w, tag=("qs-auto", gap, i, len(db[i])))
+            assert tuple(r["end"][i]) == w["end"]
