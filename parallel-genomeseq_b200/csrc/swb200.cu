@@ -611,8 +611,8 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
 // ---- query-stationary mode (sw_qs.cuh) -----------------------------------------------------------------------
 // Database search: many sequences against ONE short reference (mpi_sw_solve_uniprot.cpp: x = database protein,
 // y = query).  The matrix is computed transposed (rows = y, shared by every alignment; columns = x), see sw_qs.cuh.
-// Used when the batch is large, y fits one strip of at most 608 rows, and the scoring is tabulated (a substitution
-// matrix) or the alphabet is large (proteins);
+// Used when the batch is large (>= 2048 sequences), y fits one strip of at most 608 rows and the batch's alphabet
+// is large (proteins: more than 6 symbols);
 // SWB_QSTAT=0 / 1 forces it off / on (where applicable).  Returns 1 when the mode does not apply (caller falls back).
 int stage_qs(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_seqs, unsigned flags) {
   const HostScoring& hs = ctx->sc;
@@ -644,8 +644,9 @@ int stage_qs(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_s
   }
   const int KP = KX + 1;
   if ((size_t)KP * R * 128 > 200 * 1024) return 1;      // one profile per thread block
-  // match/mismatch scoring over a small alphabet (DNA) is served better by the batched kernels' per-warp profile
-  if (!forced && hs.match_shaped && KX <= 6) return 1;
+  // small alphabets (DNA) are served better by the batched kernels: their per-warp profile is small enough for
+  // 16-19 rows per lane and costs one LDS per cell pair instead of two
+  if (!forced && KX <= 6) return 1;
   uint32_t max_m = 0;
   uint64_t cells_ref = 0;
   for (size_t r = 0; r < n_seqs; ++r) {
