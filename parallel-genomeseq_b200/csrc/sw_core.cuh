@@ -288,7 +288,7 @@ __device__ __forceinline__ uint32_t group_max_s16x2(uint32_t v, int L) {
 }
 
 // Shared driver of both passes: restore (or initialise) the lane state, then run `nsteps` steps after
-// step t0.  All 32 lanes execute it together (full-mask shuffles); hook(k, j, E_new) fires for steps <= t1.
+// step t0.  All 32 lanes execute it together (full-mask shuffles); hook(k, c, t, j, E_new) fires for steps <= t1.
 //
 // Row strips: a pair whose sequences do not fit L*R rows is cut into nstrips strips of L*R rows (L == 32).
 // Strips run top to bottom; the last row of strip s is written to a boundary row in HBM (one packed word
