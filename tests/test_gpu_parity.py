@@ -486,3 +486,24 @@ def test_query_stationary_database_search(engine, pkg, c4_sample, monkeypatch):
                 continue
             _check(r, i, w, tag=("qs-auto", gap, i, len(db[i])))
             assert tuple(r["end"][i]) == w["end"]
+
+
+def test_reference_sharded_align_single_rank(engine, pkg):
+    """sharding.reference_sharded_align with the engine as the piece aligner (world_size 1 over gloo: one piece =
+    the whole reference): the N > 1 logic is covered on CPU (tests/test_host_cpu.py), this checks the engine glue."""
+    import torch.distributed as dist
+    sh = __import__("importlib").import_module("parallel-genomeseq_b200.sharding")
+    ref = synth.c3_reference(20_000, seed=61)
+    reads = synth.mutated_reads(ref, 6, 150, seed=62)
+    engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29641", rank=0, world_size=1)
+    try:
+        sc, ps, win = sh.reference_sharded_align(sh.engine_aligner(engine, cons_stride=400), reads, ref, 2.0, pkg.make_string_range)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    for i, x in enumerate(reads):
+        w = o.align(x, ref, mode=o.MODE_EXACT)
+        assert (int(sc[i]), int(ps[i]), int(win[i])) == (w["score"], w["pos"], 0)

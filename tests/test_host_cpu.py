@@ -112,6 +112,43 @@ assert s_all.tolist() == [3 * i + 1 for i in range(n)], rank
 assert p_all.tolist() == [i + 7 for i in range(n)], rank
 e_s, e_p = sh.gather_score_pos(score[:500].contiguous(), pos[:500].contiguous())
 assert e_s.numel() == 500 * world and e_s[500].item() == 3 * parts[1][0] + 1
+# database search: entries balanced by residues, results gathered back into entry order
+lens = np.random.default_rng(5).integers(10, 5000, size=333)
+parts = sh.balanced_partition(lens, world)
+assert sorted(torch.cat(parts).tolist()) == list(range(333))
+loads = [int(lens[p.numpy()].sum()) for p in parts]
+assert max(loads) - min(loads) <= int(lens.max())
+mine = parts[rank]
+vals = sh.gather_by_index((mine * 5 + 2).to(torch.int32), parts)
+assert vals.tolist() == [5 * i + 2 for i in range(333)], rank
+# long pairs: the reference split over the ranks, one all-reduce(max) picks the piece like the serial
+# OMPParallelLocalAligner(x, y, npiece = world, ratio) does (oracle as the stand-in aligner)
+sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+import pyoracle as o
+pkg = importlib.import_module("parallel-genomeseq_b200")
+rng = np.random.default_rng(11)
+y = "".join(rng.choice(list("ACGT"), size=3000))
+reads = []
+for k in range(12):
+    m = 150 if k < 8 else int(rng.integers(60, 200))
+    s0 = int(rng.integers(0, len(y) - m))
+    x = list(y[s0:s0 + m])
+    for q in range(m):
+        if rng.random() < 0.05:
+            x[q] = str(rng.choice(list("ACGT")))
+    reads.append("".join(x))
+reads.append("".join(rng.choice(list("ACGT"), size=90)))
+for (ma, mi, g) in ((3, -3, 2), (2, -4, 3)):
+    def piece_aligner(match, mismatch, gap):
+        def f(rs, yp):
+            w = [o.align(r, yp, mode=o.MODE_EXACT, match=match, mismatch=mismatch, gap=gap) for r in rs]
+            return [v["score"] for v in w], [v["pos"] for v in w]
+        return f
+    sc, ps, win = sh.reference_sharded_align(piece_aligner(ma, mi, g), reads, y, 2.0, pkg.make_string_range,
+                                             realign=None if (ma, mi, g) == (3, -3, 2) else piece_aligner(3, -3, 2))
+    for i, x in enumerate(reads):
+        w = o.align_chunked(x, y, world, 2.0, mode=o.MODE_EXACT, match=ma, mismatch=mi, gap=g)
+        assert (int(sc[i]), int(ps[i]), int(win[i])) == (w["score"], w["pos"], w["piece"]), (rank, i, (ma, mi, g), int(sc[i]), int(ps[i]), int(win[i]), w["score"], w["pos"], w["piece"])
 t = torch.tensor([float(rank + 1)], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # bench.py: max-over-ranks time
 assert t.item() == world
@@ -122,7 +159,9 @@ print("rank", rank, "ok")
 
 
 def test_sharding_and_gather_world_size_2_gloo(tmp_path):
-    """The N>1 path of bench.py on CPU: block partition, ragged all-gather, max-over-ranks, world_size 2, gloo."""
+    """The N>1 paths on CPU, world_size 2, gloo: block partition + ragged all-gather + max-over-ranks (bench.py),
+    residue-balanced database partition + gather by index (config 4), and the reference split over ranks with
+    an all-reduce(max) piece selection equal to the serial OMPParallelLocalAligner (config 5, oracle as aligner)."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     port = str(29500 + (os.getpid() % 2000))
