@@ -155,3 +155,45 @@ def test_live_reference_saturating_scores():
         got = o.align(x, y, mode=o.MODE_SAT_U8, match=40, mismatch=-7, gap=9)
         assert (got["score"], got["pos"], got["cx"], got["cy"]) == (want["score"], want["pos"], want["cx"], want["cy"])
         assert got["score"] == 255
+
+
+@pytest.mark.skipif(o.ref() is None or not os.path.isdir("/root/reference"), reason="compiled reference not available")
+def test_live_reference_asymmetric_table_orientation():
+    """A scoring callback with fn(a, b) != fn(b, a): pins which argument is the x (row) character and which the y
+    (column) character in the restatement — plain SWAligner and the chunked aligner (whose final alignment uses the
+    DEFAULT scoring) against the compiled reference.  The query-stationary CUDA kernels compute the
+    matrix transposed and are checked against the oracle, so this orientation must be the reference's."""
+    rng = np.random.default_rng(12)
+    alpha = list("ARNDCQEGHILKMFPSTWYV")
+    table = rng.integers(-6, 5, size=(256, 256)).astype(np.int32)
+    np.fill_diagonal(table, rng.integers(2, 9, size=256))
+    assert (table != table.T).any()
+    checked = 0
+    for _ in range(40):
+        m, n = int(rng.integers(5, 80)), int(rng.integers(30, 160))
+        if m == n:
+            n += 1
+        y = "".join(rng.choice(alpha, size=n))
+        s0 = int(rng.integers(0, max(1, n - m)))
+        x = list((y * 4)[s0:s0 + m])
+        for q in range(len(x)):
+            if rng.random() < 0.3:
+                x[q] = str(rng.choice(alpha))
+        x = "".join(x)
+        got = o.align(x, y, mode=o.MODE_EXACT, table=table, gap=3)
+        if got["score"] == 0:
+            continue
+        want = o.ref_align(x, y, smt=1, scoring_kind=2, table=table, gap=3)
+        assert (got["score"], got["pos"], got["cx"], got["cy"]) == (want["score"], want["pos"], want["cx"], want["cy"]), (m, n)
+        H = o.ref_matrix(x, y, smt=1, scoring_kind=2, table=table, gap=3).astype(np.int32)
+        assert (H == o.matrix(x, y, mode=o.MODE_EXACT, table=table, gap=3)).all()
+        checked += 1
+        if n > 4 * m and m >= 10:
+            try:
+                wantc = o.ref_align(x, y, smt=1, scoring_kind=2, table=table, gap=3, npiece=3, ratio=1.5)
+            except AssertionError:
+                continue
+            gotc = o.align_chunked(x, y, 3, 1.5, mode=o.MODE_EXACT, table=table, gap=3)
+            if gotc.get("err", 0) == 0 and gotc["score"] > 0:
+                assert (gotc["score"], gotc["pos"], gotc["cx"], gotc["cy"]) == (wantc["score"], wantc["pos"], wantc["cx"], wantc["cy"]), (m, n, "chunked")
+    assert checked >= 25
