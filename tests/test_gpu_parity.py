@@ -488,7 +488,7 @@ def test_query_stationary_database_search(engine, pkg, c4_sample, monkeypatch):
             assert tuple(r["end"][i]) == w["end"]
 
 
-def test_reference_sharded_align_single_rank(engine, pkg):
+def test_reference_sharded_align_single_rank(engine, pkg, tmp_path):
     """sharding.reference_sharded_align with the engine as the piece aligner (world_size 1 over gloo: one piece =
     the whole reference): the N > 1 logic is covered on CPU (tests/test_host_cpu.py), this checks the engine glue."""
     import torch.distributed as dist
@@ -498,7 +498,7 @@ def test_reference_sharded_align_single_rank(engine, pkg):
     engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
     created = not dist.is_initialized()
     if created:
-        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29641", rank=0, world_size=1)
+        dist.init_process_group("gloo", init_method="file://" + str(tmp_path / "rendezvous"), rank=0, world_size=1)   # no port needed
     try:
         sc, ps, win = sh.reference_sharded_align(sh.engine_aligner(engine, cons_stride=400), reads, ref, 2.0, pkg.make_string_range)
     finally:
