@@ -16,9 +16,12 @@ _ref = None
 
 
 def build_oracle(force=False):
-    src, lib = os.path.join(HERE, "sw_oracle.c"), os.path.join(HERE, "liboracle.so")
-    if force or not os.path.isfile(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-Wall", "-Wextra", "-o", lib, src])
+    """liboracle.so = the full-matrix restatement (sw_oracle.c) + the linear-memory one (sw_oracle_linear.c)."""
+    srcs = [os.path.join(HERE, "sw_oracle.c"), os.path.join(HERE, "sw_oracle_linear.c")]
+    lib = os.path.join(HERE, "liboracle.so")
+    if force or not os.path.isfile(lib) or any(os.path.getmtime(lib) < os.path.getmtime(s) for s in srcs):
+        # x86-64-v3 (AVX2): the column loops of the linear oracle vectorise; the file built here also runs on the GPU box
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fPIC", "-shared", "-std=c11", "-Wall", "-Wextra", "-o", lib] + srcs)
     return lib
 
 
@@ -27,6 +30,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build_oracle())
         _lib.swo_align.restype = C.c_int64
+        _lib.swo_align_linear.restype = C.c_int64
         _lib.swo_align_chunked.restype = C.c_int64
         _lib.swo_traceback.restype = C.c_int64
     return _lib
@@ -52,8 +56,9 @@ def saturate(v):
     return int(lib().swo_saturate(C.c_float(v)))
 
 
-def align(x, y, mode=MODE_SAT_U8, match=3, mismatch=-3, gap=2, table=None, cap=None):
-    """SWAligner<SMT>(x, y, fn, gap).calculateScore() restated.  Returns dict(score,pos,cx,cy,end)."""
+def align(x, y, mode=MODE_SAT_U8, match=3, mismatch=-3, gap=2, table=None, cap=None, linear=False):
+    """SWAligner<SMT>(x, y, fn, gap).calculateScore() restated.  Returns dict(score,pos,cx,cy,end).
+    linear=True: the linear-memory restatement (sw_oracle_linear.c) — same result, O(m + window) memory."""
     xs, ys = _u8(x), _u8(y)
     m, n = len(xs), len(ys)
     cap = cap or (m + n + 2)
@@ -65,8 +70,9 @@ def align(x, y, mode=MODE_SAT_U8, match=3, mismatch=-3, gap=2, table=None, cap=N
     else:
         t = np.ascontiguousarray(table if table is not None else default_table(match, mismatch), dtype=np.int32)
         p0, p1, g, tp = 0, 0, int(gap), _ptr(t)
-    ln = lib().swo_align(mode, _ptr(xs), C.c_int64(m), _ptr(ys), C.c_int64(n), p0, p1, tp, g,
-                         C.byref(score), C.byref(pos), C.byref(ex), C.byref(ey), _ptr(cx), _ptr(cy), C.c_int64(cap))
+    fn = lib().swo_align_linear if linear else lib().swo_align
+    ln = fn(mode, _ptr(xs), C.c_int64(m), _ptr(ys), C.c_int64(n), p0, p1, tp, g,
+            C.byref(score), C.byref(pos), C.byref(ex), C.byref(ey), _ptr(cx), _ptr(cy), C.c_int64(cap))
     if ln < 0:
         return dict(score=score.value, pos=0, cx="", cy="", end=(ex.value, ey.value), err=int(ln))
     return dict(score=score.value, pos=pos.value, cx=cx[:ln].tobytes().decode("latin-1"),

@@ -45,9 +45,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("SWB_LIB_PATH") or LIB_PATH      # SWB_LIB_PATH: A/B runs of an alternative build of the same library
+    if not os.path.isfile(path):
+        raise ImportError(f"{path} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
     lib.swb_last_error.restype = C.c_char_p
     lib.swb_version.restype = C.c_char_p
     lib.swb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]

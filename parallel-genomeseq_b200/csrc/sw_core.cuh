@@ -327,8 +327,12 @@ struct Wavefront {
       load_compare_rows<R, C>(csel, p, sp, g);
     }
   }
+  // Pass 2 may restart from a LOCAL checkpoint (the lane state a previous replay of the same strip saved into the
+  // warp's scratch, layout word w * 32 + lane) instead of a pass-1 checkpoint; per-lane pointer, null = pass 1.
+  const uint32_t* restore_from = nullptr;
   __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
     if (t0 == 0) init_state<R, C>(st, p.sc);
+    else if (restore_from) load_state<R, C, SAT>(st, p.sc, restore_from, 32, lane);
     else load_state<R, C, SAT>(st, p.sc, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
   }
   template <bool MASKED>
@@ -507,8 +511,11 @@ __device__ __forceinline__ void score_pass(Wavefront<R, C, SAT, PROFILE>& wf, co
   }
 }
 
+#ifndef SWB_SCORE_MINBLOCKS
+#define SWB_SCORE_MINBLOCKS 1
+#endif
 template <int R, int C, bool SAT, bool PROFILE>
-__global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
+__global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS) score_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -517,6 +524,7 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
   const int g = lane & (L - 1);
   const int groups_per_warp = 32 >> p.logL;
   uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+#ifndef SWB_DROP_DEAD_BRANCH
   if (p.units) {
     // pipelined strips: this warp owns ONE strip of one pair.  Producers have lower unit indices than their
     // consumers, and thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
@@ -534,6 +542,7 @@ __global__ void __launch_bounds__(128) score_kernel(const PassParams p) {
     score_pass<R, C, SAT, PROFILE, true>(wf, p, pd, (int)pd.nblk << p.logB, (int)pd.n, true);
     return;
   }
+#endif
   int pair = gwarp * groups_per_warp + (lane >> p.logL);
   const bool live = pair < p.npairs;
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
@@ -689,8 +698,11 @@ struct TraceParams {
   int ntasks;
   int mode;                   // MODE_SAT_U8: skewed raw-order tie-break; MODE_EXACT: column-major
   int max_pos;                // largest positive substitution score: a cell of score V needs row >= ceil(V / max_pos)
-  uint32_t* scratch;          // per warp: ring of the last Wc steps, word (((t & (Wc-1)) * C + c) * R + k) * 32 + lane
-  int Wc, rstride;            // ring depth in steps (power of two); rstride = C * R * L words per step and group
+  uint32_t* scratch;          // per warp: nlc local checkpoints (lane states), word (slot * state_words + w) * 32 + lane
+  int Wc, logWc;              // ring depth in steps (power of two) = period of the local checkpoints
+  int NB;                     // band: lanes per group kept in the ring (the lane of the current row and NB-1 above it)
+  int nlc;                    // local checkpoint slots per warp (power of two)
+  int ring_off;               // word offset of the rings in dynamic shared memory (after the profiles)
   int32_t* out_score;
   uint32_t* out_pos;
   uint32_t* out_end;          // 2 per task: index_x, index_y of the arg-max
@@ -750,11 +762,6 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
   const int groups_per_warp = 32 >> p.logL;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  // ring of recomputed steps, one per warp: word (((t & (Wc-1)) * C + c) * R + k) * 32 + lane, so the 32 lanes of a
-  // store are contiguous and every offset inside a step is a compile-time constant (groups of a warp may sit at
-  // different steps t; they write disjoint lanes of different ring rows)
-  constexpr uint32_t RING_STEP = (uint32_t)(C * R * 32);
-  uint32_t* scr = tp.scratch + (size_t)gwarp * tp.Wc * RING_STEP;
   const int wmask = tp.Wc - 1;
   const int G = p.sc.G;
   const int S = L * R;                 // rows per strip
@@ -901,120 +908,134 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
       }
     }
 
-    // ---- 3. traceback over a ring of recomputed columns ---------------------------------------------------
+    // ---- 3. traceback -----------------------------------------------------------------------------------------
     // SWAligner::traceback, smithwaterman.cpp:40-78, literally: compare the three neighbours' VALUES.
-    // A session replays the strip that holds row ix into the ring; the row above a strip comes from the
-    // strip's boundary row in HBM.  Leaving the ring (to the left) or the strip (upwards) starts a new session.
+    // A SESSION replays the strip that holds row ix up to the step in which (ix, iy) is computed and keeps the last
+    // Wc steps of the task's own half in a ring in SHARED memory — one byte per cell in SAT_U8 (H fits a byte), 16
+    // bits in EXACT, packed with PRMT, and only for the NB lanes at and above the lane of row ix (a walk moves up and
+    // to the left).  The group's lane 0 then walks in shared memory until it needs a cell the ring does not hold
+    // (left of the ring, above the band, or in the strip above); the next session starts there.  Every session also
+    // saves the lane state every Wc steps into the warp's scratch (local checkpoints), so a follow-up session
+    // restarts Wc..2*Wc steps back instead of at a pass-1 checkpoint up to B steps away.
+    constexpr int PW = SAT ? (R + 3) / 4 : (R + 1) / 2;       // packed ring words per lane and column
+    constexpr int SW = state_words<R, C, SAT>();
+    const int NB = tp.NB;
+    const int RW = groups_per_warp * NB;                       // ring width: band lanes of all groups of the warp
+    uint32_t* const ring = smem_prof + tp.ring_off + (size_t)warp_in_cta * ((size_t)tp.Wc * C * PW * RW);
+    uint32_t* const lck = tp.scratch + (size_t)gwarp * tp.nlc * SW * 32;
+    const uint32_t sel2 = SAT ? (half ? 0x6262u : 0x4040u) : (half ? 0x7632u : 0x5410u);
     int ix = ie, iy = je;
     uint32_t len = 0, flags = 0, pos = 0;
     uint8_t* cx = tp.out_cx + (size_t)td.out * tp.cons_cap;
     uint8_t* cy = tp.out_cy + (size_t)td.out * tp.cons_cap;
     bool done = !active;
-    bool first_session = true;
-    const int est_len = 2 * row_min + 16;
+    int lc_lo = 1, lc_hi = 0, lc_strip = -1;                   // valid local checkpoints: multiples of Wc in [lc_lo, lc_hi]
     while (!__all_sync(0xffffffffu, done)) {
-      const int ss = (ix - 1) / S;                       // strip of row ix
-      const int il = ix - ss * S;                        // row within the strip, 1..S
+      const int ss = (ix - 1) / S;                             // strip of row ix
+      const int il = ix - ss * S;                              // row within the strip, 1..S
       const int l_e = (il - 1) / R;
       const int t_hi = done ? 0 : step_of<C>(iy, l_e);
-      // restart at a checkpoint left of the columns the remaining rows can reach; the first session of a task
-      // looks back only as far as a path of twice the minimum length for its score needs (short local alignments
-      // in tall strips), later sessions the full distance
-      int look = il + 8;
-      if (first_session) look = min(look, est_len);
-      int c_lo = iy - 2 - look;
-      if (c_lo < 0) c_lo = 0;
-      const int t_lo = done ? 0 : (((c_lo / C) >> p.logB) << p.logB);
-      const int valid_lo = max(C * t_lo, C * (t_hi - tp.Wc) + 1);   // oldest column every lane still holds
+      const int band_lo = max(0, l_e - NB + 1);
       if (multi && !done && ss != cur_strip) { cur_strip = ss; wf.prepare(pd, ss, prof_warp); }
-      // ring slot of (step t, column-in-step c, row-in-lane k, lane gg of this group)
-      auto slot = [&](int t, int c, int k, int gg) -> uint32_t { return (uint32_t)(t & wmask) * RING_STEP + (uint32_t)((c * R + k) * 32) + gshift + (uint32_t)gg; };
-      if (!done && t_lo > 0) {
-        // the checkpoint itself is the last column of step t_lo for every lane
-        const uint32_t* ck = p.ckpt + pd.ck_off + wf.ck_index(pd, (t_lo >> p.logB) - 1);
-#pragma unroll
-        for (int k = 0; k < R; ++k) scr[slot(t_lo, C - 1, k, g)] = ck_reg<R, C, SAT>(p.sc, ck, L, g, k);
+      if (ss != lc_strip) { lc_lo = 1; lc_hi = 0; lc_strip = ss; }
+      // restart: the latest checkpoint (pass 1: every B steps; local: every Wc steps) at least Wc steps before t_hi
+      const int t_want = max(0, t_hi - tp.Wc);
+      int t_start = (t_want >> p.logB) << p.logB;
+      const uint32_t* from = nullptr;
+      {
+        const int t_l = min(lc_hi, (t_want >> tp.logWc) << tp.logWc);
+        if (lc_lo <= lc_hi && t_l >= lc_lo && t_l > t_start) { t_start = t_l; from = lck + (size_t)((t_l >> tp.logWc) & (tp.nlc - 1)) * SW * 32; }
       }
-      const int nsteps = warp_max_i32(t_hi - t_lo);
+      if (done) t_start = 0;
+      wf.restore_from = done ? nullptr : from;
+      const int nsteps = warp_max_i32(done ? 0 : t_hi - t_start);
+      const int t_store = max(t_start + 1, t_hi - tp.Wc + 1);  // oldest step this session leaves in the ring
+      const bool in_band = !done && g >= band_lo && g < band_lo + NB;
+      uint32_t* const ring_lane = ring + grp_in_warp * NB + (g - band_lo);
       if (tp.counters) { if (!done && g == 0) atomicAdd(tp.counters + 1, 1ull); if (lane == 0) { atomicAdd(tp.counters + 3, 1ull); atomicAdd(tp.counters + 4, (unsigned long long)nsteps); } }
-      uint32_t* const scr_lane = scr + lane;
-      // Lane g computes column j in step t = g + ceil(j / C): j >= 1 <=> t >= g + 1 (virtual columns j <= 0 hold
-      // H = 0 and are never read).  Only the last Wc steps of the session survive in the ring, so the steps
-      // before them (a session starts at a checkpoint, up to B steps early) are replayed without storing.
-      const int t_store = max(g + 1, t_hi - tp.Wc + 1);
-      wf.replay(pd, multi, t_lo, t_hi, nsteps, [&](int k, int c, int t, int, uint32_t e_new) {
-        if (t >= t_store) (scr_lane + (uint32_t)(t & wmask) * RING_STEP)[(c * R + k) * 32] = e_new;
+      uint32_t colv[C][R];
+      wf.replay(pd, multi, t_start, t_hi, nsteps,
+                [&](int k, int c, int, int, uint32_t e_new) { colv[c][k] = e_new; },
+                [&](int t, bool on, uint32_t) {
+        if (on && in_band && t >= t_store) {
+          uint32_t* dst = ring_lane + (size_t)((t & wmask) * C) * PW * RW;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (SAT) {
+#pragma unroll
+              for (int w = 0; w < PW; ++w) {                   // four rows per word: the low byte of the half (E mod 256)
+                const uint32_t a = __byte_perm(colv[c][4 * w], 4 * w + 1 < R ? colv[c][4 * w + 1] : 0u, sel2);
+                const uint32_t b = 4 * w + 2 < R ? __byte_perm(colv[c][4 * w + 2], 4 * w + 3 < R ? colv[c][4 * w + 3] : 0u, sel2) : 0u;
+                dst[(c * PW + w) * RW] = __byte_perm(a, b, 0x5410);
+              }
+            } else {
+#pragma unroll
+              for (int w = 0; w < PW; ++w)                      // two rows per word: the half's 16 bits
+                dst[(c * PW + w) * RW] = __byte_perm(colv[c][2 * w], 2 * w + 1 < R ? colv[c][2 * w + 1] : 0u, sel2);
+            }
+          }
+        }
+        if (on && (t & wmask) == 0) save_state<R, C, SAT>(wf.st, p.sc, lck + (size_t)((t >> tp.logWc) & (tp.nlc - 1)) * SW * 32, 32, lane);
       });
+      wf.restore_from = nullptr;
+      if (!done) {
+        // local checkpoints written by this session: multiples of Wc in (t_start, t_hi]; only the last nlc survive
+        const int w_lo = ((t_start >> tp.logWc) + 1) << tp.logWc, w_hi = (t_hi >> tp.logWc) << tp.logWc;
+        if (w_lo <= w_hi) {
+          const int span = tp.nlc << tp.logWc;
+          const int w_lo_eff = max(w_lo, w_hi - span + tp.Wc);
+          const bool have = lc_lo <= lc_hi;
+          if (!(have && w_lo_eff >= lc_lo && w_hi <= lc_hi)) {       // not a rewrite of checkpoints we already hold
+            int nhi = w_hi;
+            if (have && lc_lo <= w_hi + tp.Wc && lc_hi > w_hi) nhi = min(lc_hi, w_lo_eff + span - tp.Wc);
+            lc_lo = w_lo_eff; lc_hi = nhi;
+          }
+        }
+      }
       __syncwarp();
       if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 12, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
       if (g == 0 && !done) {
-        // row 0 and column 0 of H are zero and never stored; stored words are packed E = H - G.
-        // cell_ptr: address of the packed word of H(i, j) — the ring, the boundary row of the strip above, or
-        // null for the zero border.  Loads are issued together (ld.global.cg), then decoded.
-        const int row_lo = ss * S;                       // last row of the strip above (0 for strip 0)
+        const int row_lo = ss * S;                           // last row of the strip above (0 for strip 0)
         const uint32_t* above = ss > 0 ? p.bnd + pd.bnd_off + (size_t)(ss - 1) * (n + 1) : nullptr;
-        auto cell_ptr = [&](int i, int j) -> const uint32_t* {
-          if (i <= 0 || j <= 0) return nullptr;
-          if (i == row_lo) return above + j;
+        const uint32_t* ring_grp = ring + grp_in_warp * NB;
+        // H(i, j) for the walk: >= 0, or -1 when this session's ring does not hold the cell.  Row 0 and column 0 of H
+        // are zero; the row above a strip comes from its boundary row in HBM (packed E = H - G words).
+        auto cell = [&](int i, int j) -> int {
+          if (i <= 0 || j <= 0) return 0;
+          if (i == row_lo) return half_of(__ldcg(above + j), half) + G;
           const int il2 = i - row_lo - 1;
-          const int gg = il2 / R;
-          return scr + slot(step_of<C>(j, gg), (j - 1) % C, il2 - gg * R, gg);
+          const int gg = il2 / R, k = il2 - gg * R;
+          const int bl = gg - band_lo;
+          const int t = gg + (j + C - 1) / C, c = (j - 1) % C;
+          if (bl < 0 || t < t_store) return -1;
+          const uint32_t w = ring_grp[(size_t)((((t & wmask) * C + c) * PW + (SAT ? (k >> 2) : (k >> 1))) * RW) + bl];
+          return SAT ? (int)(((w >> (8 * (k & 3))) + (uint32_t)G) & 0xFFu) : (int)(int16_t)(w >> (16 * (k & 1))) + G;
         };
-        // The walk is a chain of dependent loads.  The three neighbours (and the two consensus characters) of a
-        // cell are loaded as one batch; SPEC > 1 would also fetch the next cells along the diagonal speculatively,
-        // but with every SM full of walkers the extra loads cost more than the saved round trips (measured).
-        constexpr int SPEC = 1;
-        int v1[SPEC], v2[SPEC], v3[SPEC];
-        uint8_t xb[SPEC], yb[SPEC];                          // x[ix-d-1], y[iy-d-1]: the characters the consensus emits
-        int have = 0, at = 0;                                // v*[at] belongs to the current cell when at < have
-        if (tp.dbg_flags & 2) { done = true; }
+        const int ix0 = ix, iy0 = iy;
         while (!(tp.dbg_flags & 2)) {
-          if (iy - 1 < valid_lo && iy - 1 > 0) break;        // ring exhausted: recompute further left
-          if (ix <= row_lo) break;                           // walked into the strip above
-          if (at >= have) {
-            // cells (ix-d, iy-d), d = 0..SPEC-1, as far as they stay inside the strip and the valid ring
-            const uint32_t* q1[SPEC]; const uint32_t* q2[SPEC]; const uint32_t* q3[SPEC];
-            bool okd[SPEC];
-#pragma unroll
-            for (int d = 0; d < SPEC; ++d) {
-              const int cx_ = ix - d, cy_ = iy - d;
-              okd[d] = d == 0 || (cx_ > row_lo && (cy_ - 1 >= valid_lo || cy_ - 1 <= 0) && cy_ >= 1);
-              q1[d] = okd[d] ? cell_ptr(cx_ - 1, cy_ - 1) : nullptr;
-              // the reference's second neighbour is H(ix, iy-1) and its third H(ix-1, iy); in the QS frame those
-              // are the cell above and the cell to the left
-              q2[d] = okd[d] ? (QS ? cell_ptr(cx_ - 1, cy_) : cell_ptr(cx_, cy_ - 1)) : nullptr;
-              q3[d] = okd[d] ? (QS ? cell_ptr(cx_, cy_ - 1) : cell_ptr(cx_ - 1, cy_)) : nullptr;
-            }
-            uint32_t w1[SPEC], w2[SPEC], w3[SPEC];
-#pragma unroll
-            for (int d = 0; d < SPEC; ++d) {                 // all loads first ...
-              w1[d] = q1[d] ? __ldcg(q1[d]) : p.sc.negG2; w2[d] = q2[d] ? __ldcg(q2[d]) : p.sc.negG2; w3[d] = q3[d] ? __ldcg(q3[d]) : p.sc.negG2;
-              const bool in = okd[d] && ix - d >= 1 && iy - d >= 1;
-              xb[d] = (in && tp.want_consensus) ? xraw[ix - d - 1] : (uint8_t)0;
-              yb[d] = (in && tp.want_consensus) ? yraw[iy - d - 1] : (uint8_t)0;
-            }
-#pragma unroll
-            for (int d = 0; d < SPEC; ++d) {                 // ... then decode (E = -G encodes H = 0)
-              v1[d] = okd[d] ? half_of(w1[d], half) + G : -1; v2[d] = okd[d] ? half_of(w2[d], half) + G : -1; v3[d] = okd[d] ? half_of(w3[d], half) + G : -1;
-            }
-            have = SPEC; at = 0;
-          }
-          int n1 = 0, n2 = 0, n3 = 0;
+          if (ix <= row_lo) break;                           // walked into the strip above: next session there
+          const int n1 = cell(ix - 1, iy - 1);
+          // the reference's second neighbour is H(ix, iy-1) and its third H(ix-1, iy); in the QS frame those are
+          // the cell above and the cell to the left
+          const int n2 = QS ? cell(ix - 1, iy) : cell(ix, iy - 1);
+          const int n3 = QS ? cell(ix, iy - 1) : cell(ix - 1, iy);
+          if ((n1 | n2 | n3) < 0) break;                     // left the ring: next session starts at (ix, iy)
+          const bool emit = tp.want_consensus && len < tp.cons_cap;
+          if (len >= tp.cons_cap) flags |= 1u;               // consensus truncated; the walk goes on, so pos stays exact
           uint8_t xc = 0, yc = 0;
-#pragma unroll
-          for (int d = 0; d < SPEC; ++d) if (d == at) { n1 = v1[d]; n2 = v2[d]; n3 = v3[d]; xc = xb[d]; yc = yb[d]; }
-          if (n1 < 0) { have = 0; continue; }                // speculation ran out of the safe region: reload here
-          if (len >= tp.cons_cap) { flags |= 1u; done = true; break; }
+          if (emit) { xc = xraw[ix - 1]; yc = yraw[iy - 1]; }
           const uint8_t rx = QS ? yc : xc, ry = QS ? xc : yc;   // the reference's x / y characters of this cell
           if (n1 == 0 || n2 == 0 || n3 == 0) {
-            if (tp.want_consensus) { cx[len] = rx; cy[len] = ry; }
+            if (emit) { cx[len] = rx; cy[len] = ry; }
             ++len; pos = (uint32_t)(QS ? ix : iy); done = true; break;
           }
-          if (n1 >= n2 && n1 >= n3) { if (tp.want_consensus) { cx[len] = rx; cy[len] = ry; } --ix; --iy; ++at; }
-          else if (n2 >= n1 && n2 >= n3) { if (tp.want_consensus) { cx[len] = '-'; cy[len] = ry; } if (QS) --ix; else --iy; have = 0; }
-          else { if (tp.want_consensus) { cx[len] = rx; cy[len] = '-'; } if (QS) --iy; else --ix; have = 0; }
+          if (n1 >= n2 && n1 >= n3) { if (emit) { cx[len] = rx; cy[len] = ry; } --ix; --iy; }
+          else if (n2 >= n1 && n2 >= n3) { if (emit) { cx[len] = '-'; cy[len] = ry; } if (QS) --ix; else --iy; }
+          else { if (emit) { cx[len] = rx; cy[len] = '-'; } if (QS) --iy; else --ix; }
           ++len;
         }
+        if (tp.dbg_flags & 2) done = true;
+        if (!done && ix == ix0 && iy == iy0) { flags |= 2u; done = true; }   // no progress: never expected (internal error flag)
         if (done) {
           tp.out_pos[td.out] = pos + td.pos_add;
           tp.out_len[td.out] = len;
@@ -1024,7 +1045,6 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
       __syncwarp();
       if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 13, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
       // broadcast the walker's state to its group
-      first_session = false;
       ix = __shfl_sync(0xffffffffu, ix, (int)gshift); iy = __shfl_sync(0xffffffffu, iy, (int)gshift);
       done = __shfl_sync(0xffffffffu, (int)done, (int)gshift) != 0;
     }

@@ -34,7 +34,7 @@ cudaError_t score_units_c(bool sat, bool profile, dim3 grid, dim3 block, size_t 
 template <int C>
 cudaError_t trace_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
   if (profile) return sat ? go(trace_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
-  return sat ? go(trace_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(trace_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
+  return sat ? go(trace_kernel<SWB_R, C, true, false>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, false>, grid, block, smem, st, p);   // smem: the pass-2 rings
 }
 template <int C>
 cudaError_t dump_c(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {

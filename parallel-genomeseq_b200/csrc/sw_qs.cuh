@@ -66,8 +66,10 @@ struct QsWavefront {
   __device__ __forceinline__ size_t blk_index(const PairDesc&, int b) const { return (size_t)b; }
   __device__ __forceinline__ size_t ck_index(const PairDesc&, int b) const { return (size_t)b * state_words<R, 1, SAT>() * L; }
   __device__ __forceinline__ void prepare(const PairDesc&, int, uint32_t* prof_cta) { dsel.prof = reinterpret_cast<const PT*>(prof_cta) + lane; }
+  const uint32_t* restore_from = nullptr;   // local checkpoint of pass 2 (see Wavefront::restore_from)
   __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
     if (t0 == 0) init_state<R, 1>(st, p.sc);
+    else if (restore_from) load_state<R, 1, SAT>(st, p.sc, restore_from, 32, lane);
     else load_state<R, 1, SAT>(st, p.sc, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
   }
   template <bool MASKED>

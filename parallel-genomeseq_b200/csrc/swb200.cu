@@ -165,11 +165,12 @@ bool choose_geometry(int m, size_t npairs, int r_cap, Geometry* out) {
   std::vector<Cand> c;
   int l_max = 32, l_min = 1;
   if (const char* e = getenv("SWB_FORCE_L")) { l_max = l_min = std::max(1, std::min(32, atoi(e))); }
+  const int r_forced = getenv("SWB_FORCE_R") ? atoi(getenv("SWB_FORCE_R")) : 0;
   for (int L = l_max; L >= l_min; L >>= 1) {
     const int need = (m + L - 1) / L;
     int R = 0;
     for (int i = 0; i < kNumR; ++i) if (kRSet[i] >= need && kRSet[i] <= r_cap) { R = kRSet[i]; break; }
-    if (!R) continue;
+    if (!R || (r_forced && R != r_forced)) continue;
     c.push_back({L, R, (double)m / (L * R), (double)npairs * L / 32.0});
   }
   if (c.empty()) return false;
@@ -206,6 +207,26 @@ Scoring device_scoring(const HostScoring& hs, bool force_default) {
   s.sel_and = pk(sm) ^ pk(sx);
   s.ceil2 = pk(255 - G);
   return s;
+}
+
+// Pass-2 ring geometry (sw_core.cuh, trace_body step 3): the ring of the last Wc steps lives in shared memory, packed
+// (SAT_U8: one byte per cell, EXACT: 16 bits), for the NB lanes at and above the walker's lane; nlc local checkpoints
+// of the lane state per warp live in HBM scratch.
+struct TraceGeom { int Wc, logWc, NB, nlc; size_t ring_words, scratch_words; };
+TraceGeom trace_geometry(int L, int R, int C, bool sat) {
+  const int PW = sat ? (R + 3) / 4 : (R + 1) / 2;
+  const int groups = 32 / L;
+  auto nb_for = [&](int wc) { return std::min(L, std::max(2, wc / R + 2)); };
+  auto bytes_for = [&](int wc) { return (size_t)wc * C * PW * groups * nb_for(wc) * 4; };
+  int wc = bytes_for(64) <= 16 * 1024 ? 64 : 32;
+  if (const char* e = getenv("SWB_TRACE_WC")) wc = std::max(32, std::min(256, 1 << ilog2(atoi(e))));   // >= 32: strip replays restart on 32-column chunks
+  TraceGeom t;
+  t.Wc = wc; t.logWc = ilog2(wc); t.NB = nb_for(wc);
+  if (const char* e = getenv("SWB_TRACE_NB")) t.NB = std::min(L, std::max(L > 1 ? 2 : 1, atoi(e)));
+  t.nlc = 8;
+  t.ring_words = (size_t)wc * C * PW * groups * t.NB;
+  t.scratch_words = (size_t)t.nlc * (sat ? (R + C + 1) / 2 : R + C) * 32;
+  return t;
 }
 
 // ---- kernel dispatch: one translation unit per R (sw_inst.cu compiled with -DSWB_R=<R>) ------------------
@@ -562,16 +583,18 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.ntasks = ntrace;
     tp.mode = hs.mode;
     tp.max_pos = force_default ? 3 : std::max(1, hs.max_pos);
-    int wc = 64; while (wc < L * R + ctx->C * L + 24) wc <<= 1;
-    tp.Wc = wc; tp.rstride = ctx->C * R * L;       // ring of the last Wc steps, C*R*L words per step
-    const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(uint32_t);
-    size_t max_groups = (size_t)148 * 16 * groups_per_warp;
-    max_groups = std::min(max_groups, std::max<size_t>(groups_per_warp, ((size_t)2 << 30) / per_group));
+    const TraceGeom tg = trace_geometry(L, R, ctx->C, sat);
+    tp.Wc = tg.Wc; tp.logWc = tg.logWc; tp.NB = tg.NB; tp.nlc = tg.nlc;
+    const size_t prof_words_warp = profile ? (size_t)ctx->KP * R * 32 : 0;
+    warps_per_cta = 4;
+    while (warps_per_cta > 1 && (prof_words_warp + tg.ring_words) * 4 * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
+    tp.ring_off = (int)(prof_words_warp * warps_per_cta);
+    smem = (prof_words_warp + tg.ring_words) * 4 * warps_per_cta;
+    const size_t max_groups = (size_t)148 * 16 * groups_per_warp;
     size_t groups = std::min<size_t>((size_t)ntrace, max_groups);
     size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
-    const size_t total_groups = (size_t)grid * warps_per_cta * groups_per_warp;
-    CUDA_TRY(ctx->d_scratch.ensure(total_groups * per_group));
+    CUDA_TRY(ctx->d_scratch.ensure((size_t)grid * warps_per_cta * tg.scratch_words * 4));
     tp.scratch = ctx->d_scratch.as<uint32_t>();
     tp.out_score = ctx->d_score.as<int32_t>();
     tp.out_pos = ctx->d_pos.as<uint32_t>();
@@ -777,15 +800,15 @@ int run_qs(swb_ctx* ctx) {
     tp.ntasks = (int)lc.tasks.size();
     tp.mode = hs.mode;
     tp.max_pos = std::max(1, hs.max_pos);
-    int wc = 64; while (wc < L * R + L + 24) wc <<= 1;
-    tp.Wc = wc; tp.rstride = R * L;
-    const size_t per_group = (size_t)tp.Wc * tp.rstride * sizeof(uint32_t);
-    size_t max_groups = (size_t)148 * 16 * groups_per_warp;
-    max_groups = std::min(max_groups, std::max<size_t>(groups_per_warp, ((size_t)4 << 30) / per_group));
+    const TraceGeom tg = trace_geometry(L, R, 1, sat);
+    tp.Wc = tg.Wc; tp.logWc = tg.logWc; tp.NB = tg.NB; tp.nlc = tg.nlc;
+    tp.ring_off = (int)(smem_trace / 4);                      // the rings follow the block's 16-bit profile
+    const size_t smem_trace_total = smem_trace + tg.ring_words * 4 * warps_per_cta;
+    const size_t max_groups = (size_t)148 * 16 * groups_per_warp;
     const size_t groups = std::min<size_t>(lc.tasks.size(), max_groups);
     const size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
-    CUDA_TRY(ctx->d_scratch.ensure((size_t)grid * warps_per_cta * groups_per_warp * per_group));
+    CUDA_TRY(ctx->d_scratch.ensure((size_t)grid * warps_per_cta * tg.scratch_words * 4));
     tp.scratch = ctx->d_scratch.as<uint32_t>();
     tp.out_score = ctx->d_score.as<int32_t>();
     tp.out_pos = ctx->d_pos.as<uint32_t>();
@@ -803,7 +826,7 @@ int run_qs(swb_ctx* ctx) {
     if (dbg.on) { CUDA_TRY(d_cnt.ensure(128)); CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 128, ctx->stream)); tp.counters = d_cnt.as<unsigned long long>(); }
     while (ctx->ev_pool.size() < ctx->ev_used + 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
     CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
-    CUDA_TRY(launch_qs_trace(R, sat, dim3(grid), dim3(32 * warps_per_cta), smem_trace, ctx->stream, qt));
+    CUDA_TRY(launch_qs_trace(R, sat, dim3(grid), dim3(32 * warps_per_cta), smem_trace_total, ctx->stream, qt));
     CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
     ctx->ev_used += 2;
     ctx->stats.kernel_launches++;
@@ -1035,6 +1058,8 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     if (ctx->force_l32) ctx->C = 1;
     else if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
     while (B < 65536 && words_per_block * 4.0 * ((double)max_n / ((double)B * ctx->C) + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
+    // SWB_FORCE_B: run small test batches with the checkpoint period a large batch would get (parity of the timed geometry)
+    if (const char* e = getenv("SWB_FORCE_B")) B = std::max(32, std::min(65536, 1 << ilog2(atoi(e))));
     ctx->B = B; ctx->logB = ilog2(B);
   }
   int rc = upload_profile_table(ctx);

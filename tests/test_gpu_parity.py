@@ -507,3 +507,80 @@ def test_reference_sharded_align_single_rank(engine, pkg, tmp_path):
     for i, x in enumerate(reads):
         w = o.align(x, ref, mode=o.MODE_EXACT)
         assert (int(sc[i]), int(ps[i]), int(win[i])) == (w["score"], w["pos"], 0)
+
+
+# ---- parity at the sizes and geometries that are TIMED (golden vectors of the linear-memory oracle) ---------------
+def _load_json(name):
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def c3_10k():
+    doc = _load_json("c3_10k.json")
+    ref = synth.c3_reference(doc["ref_len"])
+    assert hashlib.sha256(ref.encode()).hexdigest() == doc["ref_sha256"]
+    reads = synth.c3_reads(ref, doc["n_reads"])
+    assert hashlib.sha256("".join(reads).encode()).hexdigest() == doc["reads_sha256"]
+    return ref, reads, doc["rows"]
+
+
+def _check_rows(r, rows, idx, tag):
+    for k, i in enumerate(idx):
+        d = hashlib.sha256((r["cx"][k] + "|" + r["cy"][k]).encode()).hexdigest()[:16]
+        got = [int(r["score"][k]), int(r["pos"][k]), int(r["end"][k][0]), int(r["end"][k][1]), int(r["len"][k]), d]
+        assert got == rows[i] and r["flags"][k] == 0, (tag, i, got, rows[i])
+
+
+@pytest.mark.parametrize("B", [1024, 2048])
+def test_timed_geometry_parity(engine, pkg, c3_sample, c3_10k, monkeypatch, B):
+    """The geometry bench.py times (8 lanes x 19 rows, checkpoint period 1024 / 2048, several sub-batches that reuse
+    the HBM work buffers) on the golden C3 sample and 200 further reads — score, pos, arg-max cell, both consensus
+    strings.  The knobs only force what a 75 776-pair batch gets by itself."""
+    ref, reads, rows = c3_10k
+    monkeypatch.setenv("SWB_FORCE_L", "8")
+    monkeypatch.setenv("SWB_FORCE_R", "19")
+    monkeypatch.setenv("SWB_FORCE_B", str(B))
+    monkeypatch.setenv("SWB_CHUNK_PAIRS", "64")          # 224 reads = 112 pairs -> two sub-batches
+    engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
+    engine.set_reference(ref)
+    batch = [e["x"] for e in c3_sample["reads"]] + reads[:200]
+    r = engine.align(batch)
+    st = engine.stats()
+    assert (st["lanes_per_pair"], st["rows_per_lane"], st["block_steps"]) == (8, 19, B), st
+    for i, e in enumerate(c3_sample["reads"]):
+        _check(r, i, e, tag=("timed-geometry", B))
+    n0 = len(c3_sample["reads"])
+    sub = dict(score=r["score"][n0:], pos=r["pos"][n0:], end=r["end"][n0:], len=r["len"][n0:], flags=r["flags"][n0:], cx=r["cx"][n0:], cy=r["cy"][n0:])
+    _check_rows(sub, rows, range(200), ("timed-geometry", B))
+
+
+def test_c3_ten_thousand_reads(engine, pkg, c3_10k):
+    """BASELINE config 3 on 10 000 reads (indels included) against the linear-memory oracle's golden rows."""
+    ref, reads, rows = c3_10k
+    engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
+    engine.set_reference(ref)
+    r = engine.align(reads)
+    _check_rows(r, rows, range(len(reads)), "c3-10k")
+
+
+def test_c5_full_size(engine, pkg):
+    """BASELINE config 5 at its STATED size: 10 kbp reads against the 51 Mbp reference, EXACT (omp_sw_solve_small.cpp:167)
+    and SAT_U8 (MTSIMD, :164) — every read the golden file holds, all of score / pos / arg-max cell / consensus."""
+    doc = _load_json("c5_full.json")
+    ref = synth.c5_reference(doc["ref_len"])
+    assert hashlib.sha256(ref.encode()).hexdigest() == doc["ref_sha256"]
+    reads = synth.c5_reads(ref, 16, doc["read_len"])[:doc["n_reads"]]
+    assert [hashlib.sha256(x.encode()).hexdigest() for x in reads] == doc["reads_sha256"]
+    for mode, key in ((pkg.MODE_EXACT, "exact"), (pkg.MODE_SAT_U8, "sat_u8")):
+        engine.set_scoring_match(mode, 3, -3, 2)
+        engine.set_reference(ref)
+        r = engine.align(reads, cons_stride=25_000)
+        for i, e in enumerate(doc[key]):
+            got = (int(r["score"][i]), int(r["pos"][i]), [int(v) for v in r["end"][i]], int(r["len"][i]),
+                   hashlib.sha256(r["cx"][i].encode()).hexdigest(), hashlib.sha256(r["cy"][i].encode()).hexdigest())
+            assert got == (e["score"], e["pos"], e["end"], e["len"], e["cx_sha256"], e["cy_sha256"]), (key, i, got[:4], e["score"], e["pos"], e["end"], e["len"])
+            assert r["flags"][i] == 0

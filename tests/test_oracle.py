@@ -197,3 +197,105 @@ def test_live_reference_asymmetric_table_orientation():
             if gotc.get("err", 0) == 0 and gotc["score"] > 0:
                 assert (gotc["score"], gotc["pos"], gotc["cx"], gotc["cy"]) == (wantc["score"], wantc["pos"], wantc["cx"], wantc["cy"]), (m, n, "chunked")
     assert checked >= 25
+
+
+# ---- the linear-memory restatement (oracle/sw_oracle_linear.c) -----------------------------------------------
+def _same(a, b):
+    return (a["score"], a["pos"], a["cx"], a["cy"], a["end"], a["err"]) == (b["score"], b["pos"], b["cx"], b["cy"], b["end"], b["err"])
+
+
+def test_linear_oracle_equals_full_matrix_oracle():
+    """Differential test: anti-diagonal / three-diagonal restatement == full-matrix restatement on random shapes
+    (both orientations, related and unrelated sequences, saturating and zero-gap scorings, a random asymmetric table,
+    the all-zero case), incl. shapes large enough for several diagonal checkpoints and window doublings."""
+    rng = np.random.default_rng(2025)
+    table = rng.integers(-6, 9, size=(256, 256)).astype(np.int32)
+    for k in range(260):
+        m, n = int(rng.integers(1, 200)), int(rng.integers(1, 600))
+        if m == n:
+            n += 1
+        if k % 7 == 0:
+            m, n = n, m
+        y = "".join(rng.choice(list("ACGT"), size=n))
+        if k % 2 and m < n:
+            s = int(rng.integers(0, n - m))
+            x = "".join(c if rng.random() > 0.1 else str(rng.choice(list("ACGT"))) for c in y[s:s + m])
+        else:
+            x = "".join(rng.choice(list("ACGT"), size=m))
+        for mode in (o.MODE_SAT_U8, o.MODE_EXACT):
+            for (ma, mi, g) in ((3, -3, 2), (40, -7, 9), (5, -1, 0)):
+                kw = dict(mode=mode, match=ma, mismatch=mi, gap=g)
+                assert _same(o.align(x, y, **kw), o.align(x, y, linear=True, **kw)), (k, m, n, mode, ma, mi, g)
+        assert _same(o.align(x, y, mode=o.MODE_EXACT, table=table, gap=3), o.align(x, y, mode=o.MODE_EXACT, table=table, gap=3, linear=True))
+    assert o.align("AAAA", "CCCCCC", linear=True)["err"] == -2 == o.align("AAAA", "CCCCCC")["err"]      # SURVEY F10
+    ref = synth.c3_reference(40_000, seed=5)
+    for x in synth.mutated_reads(ref, 2, 3_000, seed=6, sub=0.02, ins=0.002, dele=0.002):
+        for mode in (o.MODE_SAT_U8, o.MODE_EXACT):
+            assert _same(o.align(x, ref, mode=mode), o.align(x, ref, mode=mode, linear=True))
+
+
+def test_linear_oracle_against_reference_goldens(data_small, random_pairs, c3_sample, c4_sample):
+    """The linear-memory restatement against the vectors dumped from the compiled reference: data_small (both SMTs),
+    the random pairs, the whole C3 sample (24 reads x 1 Mbp — the full-matrix oracle only affords 4) and the C4 sample."""
+    ref, truth = data_small
+    for name, mode, step in (("data_small_sw_skewed.csv", o.MODE_SAT_U8, 3), ("data_small_sw_float.csv", o.MODE_EXACT, 3)):
+        gold = read_golden_csv(name)
+        for (idx, _, seq, _), g in list(zip(truth, gold))[::step]:
+            r = o.align(seq, ref, mode=mode, linear=True)
+            assert (r["score"], r["pos"], r["cx"], r["cy"]) == (g["score"], g["pos"], g["cx"], g["cy"]), (name, idx)
+    for c in random_pairs:
+        if c["npiece"]:
+            continue
+        sc = c["scoring"]
+        r = o.align(c["x"], c["y"], mode=o.MODE_SAT_U8 if c["smt"] == 0 else o.MODE_EXACT, match=sc["match"], mismatch=sc["mismatch"], gap=sc["gap"], linear=True)
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (c["score"], c["pos"], c["cx"], c["cy"])
+    y = synth.c3_reference(c3_sample["ref_len"])
+    for e in c3_sample["reads"]:
+        r = o.align(e["x"], y, mode=o.MODE_SAT_U8, linear=True)
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (e["score"], e["pos"], e["cx"], e["cy"])
+    table = synth.blosum62_table()
+    for e in c4_sample["entries"]:
+        r = o.align(e["x"], c4_sample["query"], mode=o.MODE_EXACT, table=table, gap=c4_sample["gap"], linear=True)
+        assert (r["score"], r["pos"], r["cx"], r["cy"]) == (e["score"], e["pos"], e["cx"], e["cy"])
+
+
+@pytest.mark.skipif(o.ref() is None or not os.path.isdir("/root/reference"), reason="compiled reference not available")
+def test_linear_oracle_against_live_reference():
+    """Fresh shapes straight against the compiled reference (both SMTs, custom scoring)."""
+    rng = np.random.default_rng(91)
+    for _ in range(40):
+        m, n = int(rng.integers(5, 120)), int(rng.integers(20, 400))
+        if m == n:
+            n += 1
+        y = "".join(rng.choice(list("ACGT"), size=n))
+        s0 = int(rng.integers(0, max(1, n - m)))
+        x = "".join(c if rng.random() > 0.15 else str(rng.choice(list("ACGT"))) for c in (y * 3)[s0:s0 + m])
+        for smt, mode in ((0, o.MODE_SAT_U8), (1, o.MODE_EXACT)):
+            got = o.align(x, y, mode=mode, match=4, mismatch=-2, gap=3, linear=True)
+            if got["score"] == 0:
+                continue
+            want = o.ref_align(x, y, smt=smt, scoring_kind=1, match=4, mismatch=-2, gap=3)
+            assert (got["score"], got["pos"], got["cx"], got["cy"]) == (want["score"], want["pos"], want["cx"], want["cy"]), (m, n, smt)
+
+
+def test_linear_goldens_reproducible():
+    """tests/golden/c3_10k.json and c5_full.json (make_golden_linear.py) are what the current oracle computes: the
+    inputs regenerate from their seeds (sha256) and a sample of the rows is recomputed (C5 at full size is 200 s per
+    alignment, so only the C3 rows are recomputed here; the C5 file is checked for shape and seed consistency)."""
+    import json
+    with open(os.path.join(GOLDEN, "c3_10k.json")) as f:
+        c3 = json.load(f)
+    ref = synth.c3_reference(c3["ref_len"])
+    assert hashlib.sha256(ref.encode()).hexdigest() == c3["ref_sha256"]
+    reads = synth.c3_reads(ref, c3["n_reads"])
+    assert hashlib.sha256("".join(reads).encode()).hexdigest() == c3["reads_sha256"] and len(c3["rows"]) == 10_000
+    for i in range(0, 10_000, 1250):
+        w = o.align(reads[i], ref, mode=o.MODE_SAT_U8, linear=True)
+        d = hashlib.sha256((w["cx"] + "|" + w["cy"]).encode()).hexdigest()[:16]
+        assert [w["score"], w["pos"], w["end"][0], w["end"][1], len(w["cx"]), d] == c3["rows"][i], i
+    with open(os.path.join(GOLDEN, "c5_full.json")) as f:
+        c5 = json.load(f)
+    assert c5["ref_len"] == 51_000_000 and c5["n_reads"] == len(c5["exact"]) == len(c5["sat_u8"]) >= 2
+    assert all(e["score"] == 255 for e in c5["sat_u8"]) and all(25_000 < e["score"] <= 30_000 for e in c5["exact"])
+    for e in c5["exact"][:2]:
+        assert hashlib.sha256(e["cx"].encode()).hexdigest() == e["cx_sha256"] and len(e["cx"]) == e["len"]

@@ -60,6 +60,12 @@ def main():
         os.environ["SWB_CHUNK_PAIRS"] = str(rng.choice(["64", "37888"]))
         if rng.random() < 0.5:
             os.environ.pop("SWB_SELECT", None); os.environ.pop("SWB_COLS", None)
+        # pass-2 knobs: ring depth, band lanes (2 = a new session every few rows), checkpoint period
+        for k, choices in (("SWB_TRACE_WC", ["32", "64"]), ("SWB_TRACE_NB", ["2", "3", "5"]), ("SWB_FORCE_B", ["32", "64", "256", "1024"])):
+            if rng.random() < 0.4:
+                os.environ[k] = str(rng.choice(choices))
+            else:
+                os.environ.pop(k, None)
         try:
             if table is not None:
                 eng.set_scoring_table(mode, table, gap)
@@ -82,10 +88,12 @@ def main():
                 ok = (int(r["score"][i]), int(r["pos"][i]), r["cx"][i], r["cy"][i]) == (w["score"], w["pos"], w["cx"], w["cy"])
                 if ok and not npiece:
                     ok = tuple(int(v) for v in r["end"][i]) == tuple(w["end"])
+                ok = ok and int(r["flags"][i]) == 0
             checked += 1
             if not ok:
                 print("MISMATCH iter", it, "read", i, "mode", mode, "m", len(x), "n", n, "npiece", npiece, ratio, "scoring", (ma, mi, gap2) if table is None else ("table", gap),
-                      "env", {k: os.environ.get(k) for k in ("SWB_SELECT", "SWB_COLS", "SWB_CHUNK_PAIRS", "SWB_QSTAT")})
+                      "env", {k: os.environ.get(k) for k in ("SWB_SELECT", "SWB_COLS", "SWB_CHUNK_PAIRS", "SWB_QSTAT", "SWB_TRACE_WC", "SWB_TRACE_NB", "SWB_FORCE_B")})
+                print(" flags", int(r["flags"][i]))
                 print(" got ", int(r["score"][i]), int(r["pos"][i]), tuple(r["end"][i]), len(r["cx"][i]))
                 print(" want", w["score"], w["pos"], w.get("end"), len(w["cx"]))
                 sys.exit(1)
