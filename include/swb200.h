@@ -91,6 +91,13 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
 int swb_batch_run(swb_ctx* ctx, float* device_us);
 int swb_batch_fetch(swb_ctx* ctx, int32_t* score, uint32_t* pos, uint32_t* end_xy,
                     char* cons_x, char* cons_y, uint32_t* cons_len, uint32_t* out_flags);
+/*
+ * Database search (mpi_sw_solve_uniprot.cpp:95-138 aligns every database protein against the query; a search over many
+ * queries repeats that loop): swap sequence_y while the staged batch stays resident in HBM.  Only valid when the batch
+ * was staged in query-stationary mode and the new reference fits the staged lane geometry; otherwise SWB_ERR_STATE
+ * (call swb_set_reference + swb_batch_stage instead).
+ */
+int swb_batch_rebind_reference(swb_ctx* ctx, const char* y, size_t n);
 /* Device pointers of the last run's per-sequence (score, pos) arrays, n_seqs entries each (for a NCCL gather). */
 int swb_batch_device_results(swb_ctx* ctx, const int32_t** d_score, const uint32_t** d_pos);
 
@@ -104,6 +111,8 @@ typedef struct swb_stats {
   uint32_t rows_per_lane;    /* R */
   uint32_t block_steps;      /* B */
   float pass1_us, pass2_us;  /* CUDA-event split of device_us */
+  uint32_t cols_per_step;    /* C: columns a lane advances per wavefront step */
+  uint32_t kernel_kind;      /* pass-1 kernel of the (last) launch class: 0 batched, 1 pipelined strips, 2 query-stationary */
 } swb_stats;
 int swb_last_stats(const swb_ctx* ctx, swb_stats* out);
 

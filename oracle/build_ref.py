@@ -36,8 +36,10 @@ def have_reference() -> bool:
     return os.path.isfile(os.path.join(REF, "src", "aligner", "similaritymatrix.cpp"))
 
 
-def build(force: bool = False) -> str:
-    lib = os.path.join(OUT, "libref_aligner.so")
+def build(force: bool = False, useomp: bool = False) -> str:
+    """useomp=False: the SERIAL build (the oracle).  useomp=True: a second library compiled with the reference's own
+    -DUSEOMP switch (CMakeLists.txt:38-44) — its OpenMP pragmas are live; used for TIMING ONLY."""
+    lib = os.path.join(OUT, "libref_aligner_omp.so" if useomp else "libref_aligner.so")
     if not have_reference():
         if os.path.isfile(lib):
             return lib  # GPU box: prebuilt file travelled with the snapshot
@@ -58,6 +60,8 @@ def build(force: bool = False) -> str:
     cmd = ["g++", "-Ofast", "-march=x86-64-v3", "-std=c++17", "-mavx", "-ffast-math", "-ftree-loop-if-convert",
            "-fopenmp", "-fPIC", "-shared", "-include", "cstdint", "-include", "functional",
            "-I", inc, "-I", os.path.join(REF, "src", "aligner"), "-o", lib, harness] + srcs
+    if useomp:
+        cmd.insert(1, "-DUSEOMP")
     print("[build_ref]", " ".join(cmd))
     subprocess.check_call(cmd)
     return lib
@@ -65,3 +69,4 @@ def build(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, useomp=True))

@@ -215,3 +215,53 @@ def ref_bench_reads(reads, y, smt=0, npiece=0, ratio=0.0, nthreads=1):
     wall = r.ref_bench_reads(int(smt), _ptr(blob), _ptr(offs), C.c_int64(len(blobs)), _ptr(ys), C.c_int64(len(ys)),
                              int(npiece), C.c_float(ratio), int(nthreads), C.byref(us), _ptr(pos), _ptr(score))
     return wall, us.value, pos, score
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's own -DUSEOMP build (oracle/_ref/libref_aligner_omp.so): TIMING ONLY.
+# ----------------------------------------------------------------------------------------------
+_ref_omp = None
+
+
+def ref_omp():
+    global _ref_omp
+    if _ref_omp is None:
+        path = os.path.join(HERE, "_ref", "libref_aligner_omp.so")
+        if not os.path.isfile(path):
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("build_ref", os.path.join(HERE, "build_ref.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                path = mod.build(useomp=True)
+            except Exception:
+                return None
+        _ref_omp = C.CDLL(path)
+        _ref_omp.ref_omp_chunked_bench.restype = C.c_double
+        _ref_omp.ref_omp_finegrain.restype = C.c_double
+    return _ref_omp
+
+
+def ref_omp_chunked_bench(reads, y, npiece, ratio=2.0):
+    """the reference's USEOMP OMPParallelLocalAligner<Skewed>(read, ref, npiece, ratio) per read
+    (threads = npiece inside).  Returns (wall_seconds, iterate_us_sum).  Results are racy and are not returned."""
+    r = ref_omp()
+    blobs = [bytes(_u8(s)) for s in reads]
+    offs = np.zeros(len(blobs) + 1, np.int64)
+    offs[1:] = np.cumsum([len(b) for b in blobs])
+    blob = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    ys = _u8(y)
+    us = C.c_double(0)
+    wall = r.ref_omp_chunked_bench(_ptr(blob), _ptr(offs), C.c_int64(len(blobs)), _ptr(ys), C.c_int64(len(ys)), int(npiece), C.c_float(ratio), C.byref(us))
+    return wall, us.value
+
+
+def ref_omp_finegrain(x, y, finegrain_type=1, nthreads=1):
+    """SWAligner<Similarity_Matrix> with the driver-set fine-grain fields (omp_sw_solve_small.cpp:164-189).
+    Returns dict(wall, score, pos, iterate_us, adsum_us)."""
+    r = ref_omp()
+    xs, ys = _u8(x), _u8(y)
+    score, pos = C.c_float(0), C.c_uint(0)
+    t = np.zeros(2, np.float32)
+    wall = r.ref_omp_finegrain(_ptr(xs), C.c_int64(len(xs)), _ptr(ys), C.c_int64(len(ys)), int(finegrain_type), int(nthreads), C.byref(score), C.byref(pos), _ptr(t))
+    return dict(wall=wall, score=int(score.value), pos=pos.value, iterate_us=float(t[0]), adsum_us=float(t[1]))

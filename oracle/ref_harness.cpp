@@ -166,6 +166,50 @@ double ref_bench_reads(int smt, const char* reads, const int64_t* offsets, int64
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+#ifdef USEOMP
+// ---- the reference's OWN OpenMP paths (second build: -DUSEOMP -fopenmp -> oracle/_ref/libref_aligner_omp.so) -------------
+// TIMING ONLY: the USEOMP build of OMPParallelLocalAligner is racy, so nothing here
+// is ever used as an oracle.
+
+// B2: sw_solve_small.cpp:82 under USEOMP — per read, OMPParallelLocalAligner<Skewed, SWAligner<Skewed>>(read, ref, npiece,
+// ratio).calculateScore(); the reads run one after the other, the reference's pragmas use npiece threads per read
+// (plocalaligner.cpp:93,111,120).  Returns wall seconds; *iterate_us_sum = sum of getTimings()[0].
+double ref_omp_chunked_bench(const char* reads, const int64_t* offsets, int64_t n_reads, const char* y, int64_t n,
+                             int npiece, float ratio, double* iterate_us_sum) {
+  std::string_view sy(y, (size_t)n);
+  double us_sum = 0.0;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int64_t r = 0; r < n_reads; ++r) {
+    std::string_view sx(reads + offsets[r], (size_t)(offsets[r + 1] - offsets[r]));
+    OMPParallelLocalAligner<Similarity_Matrix_Skewed, SWAligner<Similarity_Matrix_Skewed>> al(sx, sy, npiece, ratio);
+    al.calculateScore();
+    us_sum += al.getTimings()[0];
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if (iterate_us_sum) *iterate_us_sum = us_sum;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// B5: omp_sw_solve_small.cpp:164-189 — SWAligner<Similarity_Matrix> with sw_finegrain_type / sw_nthreads set by the
+// driver (one "omp parallel for" per anti-diagonal, similaritymatrix.cpp:118-245).  Returns wall seconds of
+// calculateScore(); timings[0..1] = getTimings() (iterate us, sum of per-diagonal us).
+double ref_omp_finegrain(const char* x, int64_t m, const char* y, int64_t n, int finegrain_type, int nthreads,
+                         float* score, unsigned* pos, float* timings) {
+  std::string_view sx(x, (size_t)m), sy(y, (size_t)n);
+  SWAligner<Similarity_Matrix> al(sx, sy);
+  al.sw_finegrain_type = finegrain_type;
+  al.sw_nthreads = nthreads;
+  omp_set_num_threads(nthreads);
+  auto t0 = std::chrono::steady_clock::now();
+  const float s = al.calculateScore();
+  auto t1 = std::chrono::steady_clock::now();
+  if (score) *score = s;
+  if (pos) *pos = al.getPos();
+  if (timings) { auto t = al.getTimings(); timings[0] = t[0]; timings[1] = t[1]; }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+#endif  // USEOMP
+
 int ref_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

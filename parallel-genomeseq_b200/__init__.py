@@ -22,7 +22,7 @@ ERR_NAMES = {-1: "SWB_ERR_CUDA", -2: "SWB_ERR_ARG", -3: "SWB_ERR_RANGE", -4: "SW
 # every symbol include/swb200.h declares
 EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_set_scoring", "swb_set_scoring_match",
            "swb_set_reference", "swb_align_batch", "swb_batch_stage", "swb_batch_run", "swb_batch_fetch",
-           "swb_batch_device_results", "swb_last_stats", "swb_make_string_range", "swb_matrix"]
+           "swb_batch_device_results", "swb_batch_rebind_reference", "swb_last_stats", "swb_make_string_range", "swb_matrix"]
 
 
 class SwbError(RuntimeError):
@@ -34,7 +34,8 @@ class SwbError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("cells_reference", C.c_uint64), ("cells_executed", C.c_uint64), ("cells_pass2", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("lanes_per_pair", C.c_uint32), ("rows_per_lane", C.c_uint32),
-                ("block_steps", C.c_uint32), ("pass1_us", C.c_float), ("pass2_us", C.c_float)]
+                ("block_steps", C.c_uint32), ("pass1_us", C.c_float), ("pass2_us", C.c_float),
+                ("cols_per_step", C.c_uint32), ("kernel_kind", C.c_uint32)]
 
 
 _lib = None
@@ -64,6 +65,7 @@ def load_library():
     lib.swb_batch_run.argtypes = [C.c_void_p, C.c_void_p]
     lib.swb_batch_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.swb_batch_device_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.swb_batch_rebind_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.swb_last_stats.argtypes = [C.c_void_p, C.c_void_p]
     lib.swb_make_string_range.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
     lib.swb_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -149,6 +151,12 @@ class Engine:
         self.n_seqs, self.cons_stride = n, int(cons_stride)
         self.flags = FLAG_CONSENSUS if consensus else 0
         self._check(self.lib.swb_batch_stage(self.h, blob.ctypes.data, offs.ctypes.data, n, int(npiece), float(ratio), self.flags, self.cons_stride))
+
+    def rebind_reference(self, y):
+        """Swap the reference under a batch staged in query-stationary mode (database search over many queries)."""
+        yb = y.encode("latin-1") if isinstance(y, str) else bytes(y)
+        self._ref_keepalive = yb
+        self._check(self.lib.swb_batch_rebind_reference(self.h, yb, len(yb)))
 
     def run(self):
         us = C.c_float(0)

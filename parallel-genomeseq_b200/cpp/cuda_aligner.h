@@ -17,18 +17,27 @@
 //     classes derive from the reference's own LocalAligner / ParallelLocalAligner and getTimings() returns
 //     Eigen::VectorXf, so sw_solve_small.cpp:82-88 compiles unchanged after a type swap.
 //
+// Lazy batching: the reference API is one object per alignment, and one kernel launch per object would be hopeless.
+// Every shim object registers itself with its thread's Context when it is constructed; the first calculateScore() of any
+// of them aligns ALL pending objects that share its arithmetic mode, scoring, reference and chunking in ONE
+// swb_align_batch call and hands every object its own result, so a driver that constructs its aligners first and then
+// queries them (the per-read loop of sw_solve_small.cpp:56-101 split in two) runs at batch speed.  A loop that constructs,
+// queries and destroys one object at a time still gets one launch per object — use CUDABatchAligner there.
+//
 // Semantics kept from the reference: inputs are borrowed string_views that must outlive the object
 // (smithwaterman.h:48-49); consensus views point into object-owned strings; objects are not thread-safe;
 // getTimings()[0] is the time spent computing the matrix in microseconds — here DEVICE time from CUDA events.
 // Errors: the reference has none in-band (it asserts/aborts); the shims throw swb::Error.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/swb200.h"
@@ -127,7 +136,13 @@ class Context {
   }
   ~Context() { if (ctx_) swb_destroy(ctx_); }
 
+  // lazy batching (see the header comment): objects waiting for their first calculateScore()
+  void enqueue(struct Pending* p) { pending_.push_back(p); }
+  void remove(struct Pending* p) { for (size_t i = 0; i < pending_.size(); ++i) if (pending_[i] == p) { pending_.erase(pending_.begin() + i); return; } }
+  inline void flush(struct Pending* trigger);
+
  private:
+  std::vector<struct Pending*> pending_;
   void ensure() {
     if (ctx_) return;
     int dev = 0;
@@ -182,6 +197,49 @@ struct Result {
   std::string cx, cy;
   float device_us = 0.f;
 };
+}  // namespace detail
+
+// State every lazily batched aligner object shares (one alignment: x against y, optional chunking).
+struct Pending {
+  int mode = SWB_MODE_SAT_U8;
+  detail::Scoring sc;
+  std::string_view x, y;
+  int npiece = 0;
+  float ratio = 0.f;
+  detail::Result r;
+  float pass1_us = 0.f;
+  bool ready = false, queued = false;
+  std::vector<float> table;      // tabulated callback (filled when the queue is flushed)
+  Pending() = default;
+  Pending(const Pending&) = delete;
+  Pending& operator=(const Pending&) = delete;
+  void init(int m, std::string_view xs, std::string_view ys, int np, float rt) {
+    mode = m; x = xs; y = ys; npiece = np; ratio = rt;
+    Context::instance().enqueue(this); queued = true;
+  }
+  ~Pending() { if (queued) Context::instance().remove(this); }
+  // the callback's table: the two probes of similaritymatrix.cpp:389-390 in SAT_U8 mode, every byte pair in EXACT
+  void tabulate() {
+    if (!sc.is_fn || !table.empty()) return;
+    if (mode == SWB_MODE_SAT_U8) { const char A = 'A', T = 'T'; table = {sc.fn(A, A), sc.fn(A, T)}; return; }
+    table.resize(65536);
+    for (int a = 0; a < 256; ++a)
+      for (int b = 0; b < 256; ++b) { const char ca = (char)a, cb = (char)b; table[a * 256 + b] = sc.fn(ca, cb); }
+  }
+  bool same_job(Pending& o) {
+    if (mode != o.mode || npiece != o.npiece || ratio != o.ratio || sc.is_fn != o.sc.is_fn || sc.gap != o.sc.gap) return false;
+    if (y.size() != o.y.size() || (y.data() != o.y.data() && std::memcmp(y.data(), o.y.data(), y.size()) != 0)) return false;
+    if (!sc.is_fn) return sc.match == o.sc.match && sc.mismatch == o.sc.mismatch;
+    tabulate(); o.tabulate();
+    return table == o.table;
+  }
+  float calculate() {
+    if (!ready) Context::instance().flush(this);
+    return r.score;
+  }
+};
+
+namespace detail {
 inline Result run_one(int mode, const Scoring& sc, std::string_view x, std::string_view y, int npiece, float ratio) {
   Context& c = Context::instance();
   sc.apply(c, mode);
@@ -201,56 +259,95 @@ inline Result run_one(int mode, const Scoring& sc, std::string_view x, std::stri
 }
 }  // namespace detail
 
+inline void Context::flush(Pending* trigger) {
+  std::vector<Pending*> job;
+  for (Pending* p : pending_) if (p == trigger || (!p->ready && trigger->same_job(*p))) job.push_back(p);
+  if (job.empty()) job.push_back(trigger);
+  for (Pending* p : job) { remove(p); p->queued = false; }
+  trigger->sc.apply(*this, trigger->mode);
+  set_reference(trigger->y);
+  std::string blob;
+  std::vector<uint64_t> offs(job.size() + 1, 0);
+  size_t maxlen = 0;
+  for (size_t i = 0; i < job.size(); ++i) { blob.append(job[i]->x); offs[i + 1] = blob.size(); maxlen = std::max(maxlen, job[i]->x.size()); }
+  const size_t stride = 2 * maxlen + 64;
+  std::vector<int32_t> score(job.size());
+  std::vector<uint32_t> pos(job.size()), len(job.size()), flags(job.size());
+  std::vector<char> cx(job.size() * stride), cy(job.size() * stride);
+  float device_us = 0.f;
+  check(swb_align_batch(ctx_, blob.data(), offs.data(), job.size(), trigger->npiece, trigger->ratio, SWB_FLAG_CONSENSUS, score.data(), pos.data(), nullptr,
+                        cx.data(), cy.data(), len.data(), stride, flags.data(), &device_us));
+  swb_stats st{};
+  swb_last_stats(ctx_, &st);
+  for (size_t i = 0; i < job.size(); ++i) {
+    Pending* p = job[i];
+    if (flags[i] & SWB_RES_CONS_TRUNCATED) p->r = detail::run_one(p->mode, p->sc, p->x, p->y, p->npiece, p->ratio);   // a consensus longer than 2 * len + 64: alone, with room
+    else {
+      p->r.score = (float)score[i]; p->r.pos = pos[i];
+      p->r.cx.assign(cx.data() + i * stride, len[i]); p->r.cy.assign(cy.data() + i * stride, len[i]);
+    }
+    // the drivers SUM getTimings()[0] over their reads (sw_solve_small.cpp:88-89): every object gets its share of the batch
+    p->r.device_us = device_us / (float)job.size();
+    p->pass1_us = st.pass1_us / (float)job.size();
+    p->ready = true;
+  }
+}
+
 template <class SMT>
 class CUDASWAligner : public LocalAligner<SMT> {
  public:
   // the four constructors of smithwaterman.h:14-17
-  CUDASWAligner(std::string_view x, std::string_view y) : x_(x), y_(y), sm_(x, y) {}
-  CUDASWAligner(std::string_view x, std::string_view y, float gap) : x_(x), y_(y), sm_(x, y) { sc_.gap = gap; }
-  CUDASWAligner(std::string_view x, std::string_view y, ScoringFn&& fn) : x_(x), y_(y), sm_(x, y) { sc_.is_fn = true; sc_.fn = std::move(fn); }
-  CUDASWAligner(std::string_view x, std::string_view y, ScoringFn&& fn, float gap) : x_(x), y_(y), sm_(x, y) { sc_.is_fn = true; sc_.fn = std::move(fn); sc_.gap = gap; }
+  CUDASWAligner(std::string_view x, std::string_view y) : sm_(x, y) { job_.init(SMT::mode, x, y, 0, 0.f); }
+  CUDASWAligner(std::string_view x, std::string_view y, float gap) : sm_(x, y) { job_.sc.gap = gap; job_.init(SMT::mode, x, y, 0, 0.f); }
+  CUDASWAligner(std::string_view x, std::string_view y, ScoringFn&& fn) : sm_(x, y) { job_.sc.is_fn = true; job_.sc.fn = std::move(fn); job_.init(SMT::mode, x, y, 0, 0.f); }
+  CUDASWAligner(std::string_view x, std::string_view y, ScoringFn&& fn, float gap) : sm_(x, y) { job_.sc.is_fn = true; job_.sc.fn = std::move(fn); job_.sc.gap = gap; job_.init(SMT::mode, x, y, 0, 0.f); }
 
-  float calculateScore() override { r_ = detail::run_one(SMT::mode, sc_, x_, y_, 0, 0.f); return r_.score; }
-  float getScore() const override { return r_.score; }
-  unsigned int getPos() const override { return r_.pos; }
-  std::string_view getConsensus_x() const override { return r_.cx; }
-  std::string_view getConsensus_y() const override { return r_.cy; }
+  float calculateScore() override { return job_.calculate(); }
+  float getScore() const override { return job_.r.score; }
+  unsigned int getPos() const override { return job_.r.pos; }
+  std::string_view getConsensus_x() const override { return job_.r.cx; }
+  std::string_view getConsensus_y() const override { return job_.r.cy; }
   const SMT& getSimilarity_matrix() const override {
-    const detail::Scoring* sc = &sc_;
+    const detail::Scoring* sc = &job_.sc;
     sm_.apply_scoring_ = [sc](Context& c) { sc->apply(c, SMT::mode); };
     return sm_;
   }
-  TimingsVec getTimings() const override { return make_timings(r_.device_us, r_.device_us); }
+  // [0] = microseconds spent computing the matrix (the drivers' GCUPS numerator, sw_solve_small.cpp:88-89): device time of
+  // this object's share of its batch; [1] = the score-pass part of it (the reference: sum of its per-diagonal timers)
+  TimingsVec getTimings() const override { return make_timings(job_.r.device_us, job_.pass1_us); }
+  // public knobs of the reference's -DUSEOMP build that omp_sw_solve_small.cpp:165-171 sets and prints
+  // (smithwaterman.h:37-41); the CUDA path has no use for them
+  int sw_nthreads = 1, sw_finegrain_type = -1, sw_mt_simd = 0;
 
  private:
-  std::string_view x_, y_;
   mutable SMT sm_;
-  detail::Scoring sc_;
-  detail::Result r_;
+  Pending job_;
 };
 
 template <class SMT, class LAT = CUDASWAligner<SMT>>
 class CUDAParallelLocalAligner : public ParallelLocalAligner<SMT, LAT> {
  public:
   // the four constructors of plocalaligner.h:9-12
-  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio) : x_(x), y_(y), npiece_(npiece), ratio_(ratio) {}
-  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio, float gap) : x_(x), y_(y), npiece_(npiece), ratio_(ratio) { sc_.gap = gap; }
-  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio, ScoringFn&& fn) : x_(x), y_(y), npiece_(npiece), ratio_(ratio) { sc_.is_fn = true; sc_.fn = std::move(fn); }
-  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio, ScoringFn&& fn, float gap) : x_(x), y_(y), npiece_(npiece), ratio_(ratio) { sc_.is_fn = true; sc_.fn = std::move(fn); sc_.gap = gap; }
+  // The final alignment of the winning piece runs in SMT's arithmetic (LAT is only a type parameter here): the reference
+  // instantiates <Skewed, SWAligner<Skewed>> and <plain, SWAligner<plain>> (plocalaligner.cpp:145-152 also lists mixed
+  // pairs, which no driver uses); a mixed pair would silently change the score's range, so it does not compile.
+  static_assert(std::is_same<LAT, CUDASWAligner<SMT>>::value, "CUDAParallelLocalAligner: LAT must be CUDASWAligner<SMT>");
+  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio) { job_.init(SMT::mode, x, y, npiece, ratio); }
+  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio, float gap) { job_.sc.gap = gap; job_.init(SMT::mode, x, y, npiece, ratio); }
+  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio, ScoringFn&& fn) { job_.sc.is_fn = true; job_.sc.fn = std::move(fn); job_.init(SMT::mode, x, y, npiece, ratio); }
+  CUDAParallelLocalAligner(std::string_view x, std::string_view y, int npiece, float ratio, ScoringFn&& fn, float gap) { job_.sc.is_fn = true; job_.sc.fn = std::move(fn); job_.sc.gap = gap; job_.init(SMT::mode, x, y, npiece, ratio); }
 
-  float calculateScore() override { r_ = detail::run_one(SMT::mode, sc_, x_, y_, npiece_, ratio_); return r_.score; }
-  float getScore() const override { return r_.score; }
-  unsigned int getPos() const override { return r_.pos; }
-  std::string_view getConsensus_x() const override { return r_.cx; }
-  std::string_view getConsensus_y() const override { return r_.cy; }
-  TimingsVec getTimings() const override { return make_timings(r_.device_us, r_.device_us); }
+  float calculateScore() override { return job_.calculate(); }
+  float getScore() const override { return job_.r.score; }
+  unsigned int getPos() const override { return job_.r.pos; }
+  std::string_view getConsensus_x() const override { return job_.r.cx; }
+  std::string_view getConsensus_y() const override { return job_.r.cy; }
+  // plocalaligner.cpp:109-130: [0] = wall time of the piece loop, [1] = sum of the pieces' iterate times; here device
+  // time of this object's share of its batch and its score-pass part
+  TimingsVec getTimings() const override { return make_timings(job_.r.device_us, job_.pass1_us); }
 
  private:
-  std::string_view x_, y_;
-  int npiece_;
-  float ratio_;
-  detail::Scoring sc_;
-  detail::Result r_;
+  Pending job_;
 };
 
 // Batched entry point: what the rewritten driver loops call (one launch for all reads / DB entries).

@@ -78,6 +78,7 @@ struct PassParams {
   int nunits;
   uint32_t* progress;          // per unit: boundary columns published so far
   uint32_t* abort_flag;        // set when a consumer gave up waiting (never expected; avoids a hang)
+  uint32_t* ticket;            // units are handed out in the order in which warps actually start (score_units_kernel)
   int L, logL, B, logB;
   Scoring sc;
 };
@@ -161,8 +162,10 @@ __device__ __forceinline__ void step(LaneState<R, C>& st, const Select& sel, con
       cur[c + 1] = __viaddmax_s16x2(above[c + 1], sc.negG2, dG);                       // max(N - G, .) = H - G
       hook(k, c, cur[c + 1]);
     }
-    if (C == 2) bmax = __vimax3_s16x2(bmax, cur[1], cur[2]);
-    else {
+    if (C % 2 == 0) {
+#pragma unroll
+      for (int c = 0; c < C; c += 2) bmax = __vimax3_s16x2(bmax, cur[c + 1], cur[c + 2]);
+    } else {
 #pragma unroll
       for (int c = 0; c < C; ++c) bmax = __vmaxs2(bmax, cur[c + 1]);
     }
@@ -445,15 +448,22 @@ struct Wavefront {
   __device__ __forceinline__ void replay_impl(const PairDesc& pd, int t0, int t1, int nsteps, Hook&& hook, Post&& post) {
     restore(pd, t0);
     if (BND) chunk_next = load_chunk(pd, (C * t0) >> 5);  // B >= 32, so C * t0 is a multiple of 32
-    uint32_t ynext[C], ynext2[C];                          // symbols of the next two steps (loads stay two steps ahead)
-    load_symbols_m<true>(pd, t0 + 1, ynext);
-    load_symbols_m<true>(pd, t0 + 2, ynext2);
+    // symbols are loaded DEPTH steps ahead (a register queue shifted once per step): with few resident warps a step
+    // is shorter than the latency of a global load, and a two-step look-ahead left every step waiting for its symbol
+    constexpr int DEPTH = C >= 4 ? 3 : 6;
+    uint32_t yq[DEPTH][C];
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) load_symbols_m<true>(pd, t0 + 1 + d, yq[d]);
     for (int s = 1; s <= nsteps; ++s) {
       const int t = t0 + s;
       uint32_t ycur[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { ycur[c] = ynext[c]; ynext[c] = ynext2[c]; }
-      load_symbols_m<true>(pd, t + 2, ynext2);
+      for (int c = 0; c < C; ++c) {
+        ycur[c] = yq[0][c];
+#pragma unroll
+        for (int d = 0; d + 1 < DEPTH; ++d) yq[d][c] = yq[d + 1][c];
+      }
+      load_symbols_m<true>(pd, t + DEPTH, yq[DEPTH - 1]);
       const bool on = t <= t1;
       auto h = [&](int k, int c, int tt, int j, uint32_t e_new) { if (on) hook(k, c, tt, j, e_new); };
       uint32_t smax = NEG_INF2;                            // maximum over this step's cells
@@ -524,25 +534,6 @@ __global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS) score_kernel(const P
   const int g = lane & (L - 1);
   const int groups_per_warp = 32 >> p.logL;
   uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
-#ifndef SWB_DROP_DEAD_BRANCH
-  if (p.units) {
-    // pipelined strips: this warp owns ONE strip of one pair.  Producers have lower unit indices than their
-    // consumers, and thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
-    // NOTE: the host launches score_units_kernel (below) for this mode; this older in-kernel form is unreachable
-    // from the host but stays, because removing it changes the register allocation of this whole kernel and
-    // with it the schedule of the hot single-strip loop (measured 3-5 % slower; see UnitsWavefront).
-    if (gwarp >= p.nunits) return;
-    const uint2 u = p.units[gwarp];
-    const PairDesc pd = p.pairs[u.x];
-    Wavefront<R, C, SAT, PROFILE> wf(p);
-    wf.L = L; wf.g = g; wf.lane = lane;
-    wf.prepare(pd, (int)u.y, prof_warp);
-    wf.wait_on = u.y > 0 ? p.progress + (gwarp - 1) : nullptr;
-    wf.publish_to = (u.y + 1 < pd.nstrips) ? p.progress + gwarp : nullptr;
-    score_pass<R, C, SAT, PROFILE, true>(wf, p, pd, (int)pd.nblk << p.logB, (int)pd.n, true);
-    return;
-  }
-#endif
   int pair = gwarp * groups_per_warp + (lane >> p.logL);
   const bool live = pair < p.npairs;
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
@@ -573,8 +564,8 @@ __global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS) score_kernel(const P
 // ======================================================================================================
 // Pipelined strips (few long pairs): one warp per (pair, strip) unit, the strips of a pair run concurrently.
 // A strip reads the boundary row of the strip above as soon as that strip has published it (progress
-// counters), 32 columns per coalesced load.  Producers have lower unit indices than their consumers, and
-// thread blocks start in index order, so a waiting strip never keeps its producer off the GPU.
+// counters), 32 columns per coalesced load.  Producers have lower unit indices than their consumers, and units are
+// handed out by an atomic ticket in the order in which warps start, so a waiting strip's producer is always resident.
 //
 // This path has a kernel and a stepping routine of its own (UnitsWavefront adds to Wavefront, it changes
 // nothing in it): ptxas allocates registers and schedules per kernel, and the batched kernel above is
@@ -586,6 +577,7 @@ template <int R, int C, bool SAT, bool PROFILE>
 struct UnitsWavefront : Wavefront<R, C, SAT, PROFILE> {
   using Base = Wavefront<R, C, SAT, PROFILE>;
   bool writer = false;     // lane 31 of a strip that has a strip below it
+  uint32_t chunk_next2 = 0;   // boundary chunks are fetched TWO chunks (64 columns) ahead of their use
   __device__ __forceinline__ UnitsWavefront(const PassParams& p_) : Base(p_) {}
 
   template <bool MASKED, class Sel>
@@ -595,7 +587,7 @@ struct UnitsWavefront : Wavefront<R, C, SAT, PROFILE> {
     for (int c = 0; c < C; ++c) {
       upv[c] = __shfl_up_sync(0xffffffffu, this->st.bot[c], 1);
       const int base = C * (t - 1);                       // 0-based column of lane 0's first column in this step
-      if (c == 0 && (base & 31) == 0) { this->chunk_cur = this->chunk_next; this->chunk_next = this->load_chunk(pd, (base >> 5) + 1); }
+      if (c == 0 && (base & 31) == 0) { this->chunk_cur = this->chunk_next; this->chunk_next = chunk_next2; chunk_next2 = this->load_chunk(pd, (base >> 5) + 2); }
       const uint32_t north = __shfl_sync(0xffffffffu, this->chunk_cur, (base & 31) + c);
       if (this->lane == 0) upv[c] = north;
     }
@@ -641,8 +633,12 @@ __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+  // Atomic ticket: a warp takes the next unit when it STARTS, so the producer of its unit (the unit before it) is
+  // always resident already and forward progress never depends on the order in which thread blocks are dispatched.
+  int gwarp = 0;
+  if (lane == 0) gwarp = (int)atomicAdd(p.ticket, 1u);
+  gwarp = __shfl_sync(0xffffffffu, gwarp, 0);
   if (gwarp >= p.nunits) return;
   const uint2 u = p.units[gwarp];
   const PairDesc pd = p.pairs[u.x];
@@ -661,6 +657,7 @@ __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
   const int pub_every = max(1, min(16, (int)sqrtf(0.1f * (float)nb / (float)max(1u, pd.nstrips))));
   int since_pub = 0;
   wf.template begin<true>(pd, 0);
+  wf.chunk_next2 = wf.load_chunk(pd, 1);
   uint32_t bmax = NEG_INF2;
   for (int b = 0; b < nb; ++b) {
     const int t0 = b << p.logB;
@@ -918,10 +915,15 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
     // saves the lane state every Wc steps into the warp's scratch (local checkpoints), so a follow-up session
     // restarts Wc..2*Wc steps back instead of at a pass-1 checkpoint up to B steps away.
     constexpr int PW = SAT ? (R + 3) / 4 : (R + 1) / 2;       // packed ring words per lane and column
+    constexpr int EPW = SAT ? 4 : 2;                           // ring elements (cells) per word
+    constexpr int RP = PW * EPW;                               // element slots per lane: R rounded up to whole words
     constexpr int SW = state_words<R, C, SAT>();
     const int NB = tp.NB;
-    const int RW = groups_per_warp * NB;                       // ring width: band lanes of all groups of the warp
-    uint32_t* const ring = smem_prof + tp.ring_off + (size_t)warp_in_cta * ((size_t)tp.Wc * C * PW * RW);
+    const int cmask = tp.Wc * C - 1;                           // ring columns - 1 (Wc and C are powers of two)
+    const int cstride = NB * PW;                               // words per ring column: the band's rows, lane by lane
+    // this group's ring: word ((j - 1) & cmask) * cstride + (lane - band_lo) * PW + w  (indexed by COLUMN, so that the
+    // walker's address is a multiply-add of its own coordinates; lane g of a step stores column t - g)
+    uint32_t* const ring = smem_prof + tp.ring_off + ((size_t)warp_in_cta * groups_per_warp + grp_in_warp) * ((size_t)(cmask + 1) * cstride);
     uint32_t* const lck = tp.scratch + (size_t)gwarp * tp.nlc * SW * 32;
     const uint32_t sel2 = SAT ? (half ? 0x6262u : 0x4040u) : (half ? 0x7632u : 0x5410u);
     int ix = ie, iy = je;
@@ -951,27 +953,27 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
       const int nsteps = warp_max_i32(done ? 0 : t_hi - t_start);
       const int t_store = max(t_start + 1, t_hi - tp.Wc + 1);  // oldest step this session leaves in the ring
       const bool in_band = !done && g >= band_lo && g < band_lo + NB;
-      uint32_t* const ring_lane = ring + grp_in_warp * NB + (g - band_lo);
+      uint32_t* const ring_lane = ring + (g - band_lo) * PW;
       if (tp.counters) { if (!done && g == 0) atomicAdd(tp.counters + 1, 1ull); if (lane == 0) { atomicAdd(tp.counters + 3, 1ull); atomicAdd(tp.counters + 4, (unsigned long long)nsteps); } }
-      uint32_t colv[C][R];
-      wf.replay(pd, multi, t_start, t_hi, nsteps,
-                [&](int k, int c, int, int, uint32_t e_new) { colv[c][k] = e_new; },
-                [&](int t, bool on, uint32_t) {
+      uint32_t colv[C][R];                                     // the step's cells per column (C > 1; with C == 1 they are the lane state)
+      auto keep = [&](int k, int c, int, int, uint32_t e_new) { if (C > 1) colv[c][k] = e_new; };
+      wf.replay(pd, multi, t_start, t_hi, nsteps, keep, [&](int t, bool on, uint32_t) {
         if (on && in_band && t >= t_store) {
-          uint32_t* dst = ring_lane + (size_t)((t & wmask) * C) * PW * RW;
 #pragma unroll
           for (int c = 0; c < C; ++c) {
+            const uint32_t* v = C == 1 ? wf.st.E : colv[c];
+            uint32_t* dst = ring_lane + ((col_of<C>(t, g, c) - 1) & cmask) * cstride;
             if (SAT) {
 #pragma unroll
               for (int w = 0; w < PW; ++w) {                   // four rows per word: the low byte of the half (E mod 256)
-                const uint32_t a = __byte_perm(colv[c][4 * w], 4 * w + 1 < R ? colv[c][4 * w + 1] : 0u, sel2);
-                const uint32_t b = 4 * w + 2 < R ? __byte_perm(colv[c][4 * w + 2], 4 * w + 3 < R ? colv[c][4 * w + 3] : 0u, sel2) : 0u;
-                dst[(c * PW + w) * RW] = __byte_perm(a, b, 0x5410);
+                const uint32_t a = __byte_perm(v[4 * w], 4 * w + 1 < R ? v[4 * w + 1] : 0u, sel2);
+                const uint32_t b = 4 * w + 2 < R ? __byte_perm(v[4 * w + 2], 4 * w + 3 < R ? v[4 * w + 3] : 0u, sel2) : 0u;
+                dst[w] = __byte_perm(a, b, 0x5410);
               }
             } else {
 #pragma unroll
               for (int w = 0; w < PW; ++w)                      // two rows per word: the half's 16 bits
-                dst[(c * PW + w) * RW] = __byte_perm(colv[c][2 * w], 2 * w + 1 < R ? colv[c][2 * w + 1] : 0u, sel2);
+                dst[w] = __byte_perm(v[2 * w], 2 * w + 1 < R ? v[2 * w + 1] : 0u, sel2);
             }
           }
         }
@@ -997,29 +999,36 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
       if (g == 0 && !done) {
         const int row_lo = ss * S;                           // last row of the strip above (0 for strip 0)
         const uint32_t* above = ss > 0 ? p.bnd + pd.bnd_off + (size_t)(ss - 1) * (n + 1) : nullptr;
-        const uint32_t* ring_grp = ring + grp_in_warp * NB;
-        // H(i, j) for the walk: >= 0, or -1 when this session's ring does not hold the cell.  Row 0 and column 0 of H
-        // are zero; the row above a strip comes from its boundary row in HBM (packed E = H - G words).
+        const int i_min = row_lo + band_lo * R + 1;          // first row the ring holds
+        const int j_min = C * (t_store - band_lo - 1) + 1;   // first column EVERY band lane holds (lane g holds t_store - g onwards)
+        // H(i, j) from the ring (both inside it): one byte (SAT_U8: E mod 256) or one signed 16-bit (EXACT: E) load
+        auto ring_val = [&](int i, int j) -> int {
+          const int r = i - i_min;
+          const int e = (RP == R) ? r : r + (r / R) * (RP - R);          // rows of a lane are padded to whole words
+          const int col = ((j - 1) & cmask) * cstride;
+          if (SAT) return (int)((reinterpret_cast<const uint8_t*>(ring)[col * 4 + e] + (uint32_t)G) & 0xFFu);
+          return (int)reinterpret_cast<const int16_t*>(ring)[col * 2 + e] + G;
+        };
+        // any cell: the zero border, the boundary row of the strip above (HBM, packed E words), the ring, or -1 when
+        // this session does not hold it
         auto cell = [&](int i, int j) -> int {
           if (i <= 0 || j <= 0) return 0;
           if (i == row_lo) return half_of(__ldcg(above + j), half) + G;
-          const int il2 = i - row_lo - 1;
-          const int gg = il2 / R, k = il2 - gg * R;
-          const int bl = gg - band_lo;
-          const int t = gg + (j + C - 1) / C, c = (j - 1) % C;
-          if (bl < 0 || t < t_store) return -1;
-          const uint32_t w = ring_grp[(size_t)((((t & wmask) * C + c) * PW + (SAT ? (k >> 2) : (k >> 1))) * RW) + bl];
-          return SAT ? (int)(((w >> (8 * (k & 3))) + (uint32_t)G) & 0xFFu) : (int)(int16_t)(w >> (16 * (k & 1))) + G;
+          if (i < i_min || j < j_min) return -1;
+          return ring_val(i, j);
         };
         const int ix0 = ix, iy0 = iy;
         while (!(tp.dbg_flags & 2)) {
           if (ix <= row_lo) break;                           // walked into the strip above: next session there
-          const int n1 = cell(ix - 1, iy - 1);
-          // the reference's second neighbour is H(ix, iy-1) and its third H(ix-1, iy); in the QS frame those are
-          // the cell above and the cell to the left
-          const int n2 = QS ? cell(ix - 1, iy) : cell(ix, iy - 1);
-          const int n3 = QS ? cell(ix, iy - 1) : cell(ix - 1, iy);
-          if ((n1 | n2 | n3) < 0) break;                     // left the ring: next session starts at (ix, iy)
+          int vd, vu, vl;                                    // H(ix-1, iy-1), H(ix-1, iy), H(ix, iy-1)
+          if (ix - 1 >= i_min && iy - 1 >= j_min) { vd = ring_val(ix - 1, iy - 1); vu = ring_val(ix - 1, iy); vl = ring_val(ix, iy - 1); }
+          else {
+            vd = cell(ix - 1, iy - 1); vu = cell(ix - 1, iy); vl = cell(ix, iy - 1);
+            if ((vd | vu | vl) < 0) break;                   // left the ring: next session starts at (ix, iy)
+          }
+          // the reference's second neighbour is H(ix, iy-1) and its third H(ix-1, iy); in the QS frame (transposed)
+          // those are the cell above and the cell to the left
+          const int n1 = vd, n2 = QS ? vu : vl, n3 = QS ? vl : vu;
           const bool emit = tp.want_consensus && len < tp.cons_cap;
           if (len >= tp.cons_cap) flags |= 1u;               // consensus truncated; the walk goes on, so pos stays exact
           uint8_t xc = 0, yc = 0;

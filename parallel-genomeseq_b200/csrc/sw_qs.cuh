@@ -112,14 +112,16 @@ struct QsWavefront {
   template <class Hook, class Post>
   __device__ __forceinline__ void replay(const PairDesc& pd, bool, int t0, int t1, int nsteps, Hook&& hook, Post&& post) {
     restore(pd, t0);
-    uint32_t na, nb, na2, nb2;
-    load_codes<true>(pd, t0 + 1, na, nb);
-    load_codes<true>(pd, t0 + 2, na2, nb2);
+    constexpr int DEPTH = 6;                               // look-ahead of the column codes, see Wavefront::replay_impl
+    uint32_t qa[DEPTH], qb[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) load_codes<true>(pd, t0 + 1 + d, qa[d], qb[d]);
     for (int s = 1; s <= nsteps; ++s) {
       const int t = t0 + s;
-      const uint32_t ca = na, cb = nb;
-      na = na2; nb = nb2;
-      load_codes<true>(pd, t + 2, na2, nb2);
+      const uint32_t ca = qa[0], cb = qb[0];
+#pragma unroll
+      for (int d = 0; d + 1 < DEPTH; ++d) { qa[d] = qa[d + 1]; qb[d] = qb[d + 1]; }
+      load_codes<true>(pd, t + DEPTH, qa[DEPTH - 1], qb[DEPTH - 1]);
       const bool on = t <= t1;
       auto h = [&](int k, int c, int tt, int j, uint32_t e_new) { if (on) hook(k, c, tt, j, e_new); };
       uint32_t smax = NEG_INF2;

@@ -110,6 +110,8 @@ struct swb_ctx {
   // query-stationary mode (sw_qs.cuh): database search against a short reference, computed transposed
   bool qs = false;
   int qs_KP = 0;
+  uint64_t batch_residues = 0, batch_max_m = 0;   // of the staged batch (swb_batch_rebind_reference)
+  bool wide = false;                  // EXACT scores beyond the 16-bit lanes: one alignment per 32-bit lane
   DevBuf d_xcode, d_qs_table;
   swb_stats stats{};
   std::vector<cudaEvent_t> ev_pool;   // event pairs around every pass-2 launch of the current run
@@ -216,7 +218,8 @@ struct TraceGeom { int Wc, logWc, NB, nlc; size_t ring_words, scratch_words; };
 TraceGeom trace_geometry(int L, int R, int C, bool sat) {
   const int PW = sat ? (R + 3) / 4 : (R + 1) / 2;
   const int groups = 32 / L;
-  auto nb_for = [&](int wc) { return std::min(L, std::max(2, wc / R + 2)); };
+  // a diagonal walk of Wc columns climbs Wc rows: the walker's lane plus ceil(Wc / R) lanes above it
+  auto nb_for = [&](int wc) { return std::min(L, std::max(2, (wc + R - 1) / R + 1)); };
   auto bytes_for = [&](int wc) { return (size_t)wc * C * PW * groups * nb_for(wc) * 4; };
   int wc = bytes_for(64) <= 16 * 1024 ? 64 : 32;
   if (const char* e = getenv("SWB_TRACE_WC")) wc = std::max(32, std::min(256, 1 << ilog2(atoi(e))));   // >= 32: strip replays restart on 32-column chunks
@@ -299,6 +302,41 @@ int upload_profile_table(swb_ctx* ctx) {
   return SWB_OK;
 }
 
+// Rows per lane of the strip geometry (L = 32) for a batch whose longest sequence has m_max rows.  With few long
+// pairs (the long-pair config) the strips of a pair run concurrently, one warp each, so thin strips are preferred — as
+// thin as the HBM budget for the strip boundary rows allows — to put a warp on every SM sub-partition; *few_long tells
+// the caller that this mode applies.
+int strip_rows(const swb_ctx* ctx, uint32_t m_max, uint32_t n_max, size_t npairs_est, bool profile, bool* few_long) {
+  const int r_hard = profile ? std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128)))) : 32;
+  const int r_pref = profile ? std::max(2, std::min(r_hard, (int)(14336 / ((size_t)ctx->KP * 128)))) : 32;
+  int r_strip = kRSet[0];
+  const int cap = profile ? r_pref : 32;
+  for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= cap) r_strip = kRSet[i];
+  if (few_long) *few_long = false;
+  if (npairs_est < 148 * 8 && (int)m_max > 32 * r_strip) {
+    if (few_long) *few_long = true;
+    // boundary rows: up to half of the free HBM (at least 32 GiB), SWB_BND_BUDGET_MB overrides
+    size_t budget_mb = 32768;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget_mb = std::max<size_t>(budget_mb, (free_b + ctx->d_bnd.cap) / 2 / 1048576);
+    if (const char* e = getenv("SWB_BND_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
+    for (int i = kNumR - 1; i >= 0; --i) {
+      const int R = kRSet[i];
+      if (R > r_strip || R < 4) continue;
+      const double strips = std::ceil((double)m_max / (32.0 * R));
+      const double bytes = (strips - 1) * ((double)n_max + 1) * 4.0 * (double)npairs_est;
+      if (bytes > (double)budget_mb * 1048576.0) break;
+      r_strip = R;
+      if (strips * (double)npairs_est >= 148.0 * 4.0) break;      // one warp per SM sub-partition is enough
+    }
+  }
+  if (const char* e = getenv("SWB_STRIP_R")) {
+    const int want = std::max(2, std::min(r_hard, atoi(e)));
+    for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= want) r_strip = kRSet[i];
+  }
+  return r_strip;
+}
+
 struct TaskSeed { uint32_t read; uint32_t piece; uint32_t y_off; uint32_t n; uint32_t m; uint32_t x_off; };
 
 // Build launch classes from task seeds (task id = position in `seeds`, grouped by read: pieces contiguous).
@@ -313,33 +351,9 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
   std::map<uint32_t, size_t> count_by_m;
   for (auto& s : seeds) count_by_m[s.m]++;
   std::map<uint32_t, Geometry> geo_by_m;
-  int r_strip = kRSet[0];            // rows per lane of the strip geometry (L = 32)
-  {
-    int cap = profile ? r_pref : 32;
-    for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= cap) r_strip = kRSet[i];
-    // few long pairs (the long-pair config): the strips of a pair run concurrently, one warp each, so prefer
-    // thin strips — as thin as the HBM budget for the boundary rows allows — to put a warp on every SM sub-partition
-    uint32_t m_max = 0, n_max = 0;
-    for (auto& sd : seeds) { m_max = std::max(m_max, sd.m); n_max = std::max(n_max, sd.n); }
-    const size_t npairs_est = (seeds.size() + 1) / 2;
-    if (npairs_est < 148 * 8 && (int)m_max > 32 * r_strip) {
-      size_t budget_mb = 32768;
-      if (const char* e = getenv("SWB_BND_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
-      for (int i = kNumR - 1; i >= 0; --i) {
-        const int R = kRSet[i];
-        if (R > r_strip || R < 4) continue;
-        const double strips = std::ceil((double)m_max / (32.0 * R));
-        const double bytes = (strips - 1) * ((double)n_max + 1) * 4.0 * (double)npairs_est;
-        if (bytes > (double)budget_mb * 1048576.0) break;
-        r_strip = R;
-        if (strips * (double)npairs_est >= 148.0 * 4.0) break;      // one warp per SM sub-partition is enough
-      }
-    }
-    if (const char* e = getenv("SWB_STRIP_R")) {
-      const int want = std::max(2, std::min(r_hard, atoi(e)));
-      for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= want) r_strip = kRSet[i];
-    }
-  }
+  uint32_t m_max = 0, n_max = 0;
+  for (auto& sd : seeds) { m_max = std::max(m_max, sd.m); n_max = std::max(n_max, sd.n); }
+  int r_strip = strip_rows(ctx, m_max, n_max, (seeds.size() + 1) / 2, profile, nullptr);   // rows per lane of the strip geometry (L = 32)
   // Geometry per distinct length.  First pass: the best (L, R) for every length on its own.
   const int r_cap = profile ? std::max(r_pref, kRSet[0]) : 32;
   std::map<std::pair<int, int>, size_t> tasks_per_geo;
@@ -524,20 +538,21 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
       size_t total_units = 0;
       for (auto& pd : lc.pairs) total_units += pd.nstrips;
       const bool pipelined = L == 32 && lc.max_strips > 1 && lc.pairs.size() < 148 * 8 && !getenv("SWB_NO_PIPELINE");
-      pp.units = nullptr; pp.nunits = 0; pp.progress = nullptr; pp.abort_flag = nullptr;
+      pp.units = nullptr; pp.nunits = 0; pp.progress = nullptr; pp.abort_flag = nullptr; pp.ticket = nullptr;
       if (pipelined) {
         std::vector<uint2> units;
         units.reserve(total_units);
         for (size_t pi = 0; pi < lc.pairs.size(); ++pi)
           for (uint32_t st = 0; st < lc.pairs[pi].nstrips; ++st) units.push_back(make_uint2((unsigned)pi, st));
         CUDA_TRY(ctx->d_units.ensure(units.size() * sizeof(uint2)));
-        CUDA_TRY(ctx->d_progress.ensure((units.size() + 1) * 4));
+        CUDA_TRY(ctx->d_progress.ensure((units.size() + 2) * 4));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_units.p, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(ctx->d_progress.p, 0, (units.size() + 1) * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_progress.p, 0, (units.size() + 2) * 4, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));      // `units` is a host temporary
         pp.units = ctx->d_units.as<uint2>(); pp.nunits = (int)units.size();
         pp.progress = ctx->d_progress.as<uint32_t>();
         pp.abort_flag = ctx->d_progress.as<uint32_t>() + units.size();
+        pp.ticket = ctx->d_progress.as<uint32_t>() + units.size() + 1;
         warps = units.size();
         warps_per_cta = 1;                                   // spread the units over all SMs
         if (profile) smem = (size_t)ctx->KP * R * 32 * 4;
@@ -590,6 +605,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     while (warps_per_cta > 1 && (prof_words_warp + tg.ring_words) * 4 * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
     tp.ring_off = (int)(prof_words_warp * warps_per_cta);
     smem = (prof_words_warp + tg.ring_words) * 4 * warps_per_cta;
+    if (smem > 220 * 1024) return fail(ctx, SWB_ERR_UNSUPPORTED, "pass-2 ring does not fit shared memory (lower SWB_TRACE_WC / SWB_TRACE_NB)");
     const size_t max_groups = (size_t)148 * 16 * groups_per_warp;
     size_t groups = std::min<size_t>((size_t)ntrace, max_groups);
     size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
@@ -626,6 +642,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     }
     ctx->stats.cells_pass2 += (uint64_t)ntrace * (uint64_t)(3 * ctx->B * ctx->C + lc.max_m + 16) * L * R * 2ull;
     ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
+    ctx->stats.cols_per_step = ctx->C; ctx->stats.kernel_kind = (L == 32 && lc.max_strips > 1 && lc.pairs.size() < 148 * 8 && !getenv("SWB_NO_PIPELINE")) ? 1u : 0u;
   }
   return SWB_OK;
 }
@@ -751,6 +768,7 @@ int stage_qs(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_s
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));          // codes / t are host temporaries
   ctx->qs = true; ctx->qs_KP = KP;
+  ctx->batch_residues = blob; ctx->batch_max_m = max_m;
   ctx->stats = swb_stats{};
   ctx->stats.cells_reference = cells_ref;
   return SWB_OK;
@@ -782,7 +800,7 @@ int run_qs(swb_ctx* ctx) {
     qp.m = (int)ctx->y.size();
     const size_t smem = (size_t)ctx->qs_KP * R * 32 * 4;      // score pass: 32-bit profile, one per thread block
     const size_t smem_trace = smem / 2;                       // pass 2: 16-bit profile
-    const int warps_per_cta = 4;
+    int warps_per_cta = 4;
     {
       const size_t warps = (lc.pairs.size() + groups_per_warp - 1) / groups_per_warp;
       const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
@@ -803,7 +821,9 @@ int run_qs(swb_ctx* ctx) {
     const TraceGeom tg = trace_geometry(L, R, 1, sat);
     tp.Wc = tg.Wc; tp.logWc = tg.logWc; tp.NB = tg.NB; tp.nlc = tg.nlc;
     tp.ring_off = (int)(smem_trace / 4);                      // the rings follow the block's 16-bit profile
+    while (warps_per_cta > 1 && smem_trace + tg.ring_words * 4 * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
     const size_t smem_trace_total = smem_trace + tg.ring_words * 4 * warps_per_cta;
+    if (smem_trace_total > 220 * 1024) return fail(ctx, SWB_ERR_UNSUPPORTED, "pass-2 ring does not fit shared memory (lower SWB_TRACE_WC / SWB_TRACE_NB)");
     const size_t max_groups = (size_t)148 * 16 * groups_per_warp;
     const size_t groups = std::min<size_t>(lc.tasks.size(), max_groups);
     const size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
@@ -840,6 +860,7 @@ int run_qs(swb_ctx* ctx) {
     }
     ctx->stats.cells_pass2 += (uint64_t)lc.tasks.size() * (uint64_t)(3 * ctx->B + lc.max_m + 16) * L * R * 2ull;
     ctx->stats.lanes_per_pair = L; ctx->stats.rows_per_lane = R; ctx->stats.block_steps = ctx->B;
+    ctx->stats.cols_per_step = 1; ctx->stats.kernel_kind = 2u;
   }
   return SWB_OK;
 }
@@ -926,8 +947,32 @@ int swb_set_scoring_match(swb_ctx* ctx, int mode, float match, float mismatch, f
   return swb_set_scoring(ctx, mode, t.data(), gap);
 }
 
+static int set_reference_impl(swb_ctx* ctx, const char* y, size_t n);
+
 int swb_set_reference(swb_ctx* ctx, const char* y, size_t n) {
   if (!ctx || (!y && n)) return SWB_ERR_ARG;
+  const int rc = set_reference_impl(ctx, y, n);
+  if (rc == SWB_OK) ctx->staged = false;
+  return rc;
+}
+
+// Database search runs MANY references (queries) against ONE staged batch (mpi_sw_solve_uniprot.cpp: every query meets
+// the whole database): when the batch is staged in query-stationary mode, its HBM-resident sequences, pairing and work
+// buffers do not depend on the reference, only the kernel's row count does.  Swaps the reference without re-staging.
+int swb_batch_rebind_reference(swb_ctx* ctx, const char* y, size_t n) {
+  if (!ctx || !y || n == 0) return SWB_ERR_ARG;
+  if (!ctx->staged || !ctx->qs || ctx->classes.empty()) return fail(ctx, SWB_ERR_STATE, "rebind needs a batch staged in query-stationary mode");
+  const Geometry& geo = ctx->classes[0].geo;
+  if (n > (size_t)geo.L * geo.R) return fail(ctx, SWB_ERR_STATE, "the new reference does not fit the staged lane geometry (stage again)");
+  const uint64_t reach = std::min<uint64_t>(ctx->batch_max_m, n) * (uint64_t)std::max(1, ctx->sc.max_pos) + (uint64_t)ctx->sc.G + 16;
+  if (ctx->sc.mode == SWB_MODE_EXACT && reach > 32000) return fail(ctx, SWB_ERR_STATE, "the new reference may leave the 16-bit lane range (stage again)");
+  const int rc = set_reference_impl(ctx, y, n);
+  if (rc != SWB_OK) { ctx->staged = false; return rc; }
+  ctx->stats.cells_reference = ctx->batch_residues * (uint64_t)n;
+  return SWB_OK;
+}
+
+static int set_reference_impl(swb_ctx* ctx, const char* y, size_t n) {
   if (n == 0) return fail(ctx, SWB_ERR_ARG, "empty reference");
   if (n > 0x7FF00000ull) return fail(ctx, SWB_ERR_UNSUPPORTED, "reference longer than 2^31 - 2^20 (step counters are 32-bit)");
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -948,7 +993,6 @@ int swb_set_reference(swb_ctx* ctx, const char* y, size_t n) {
   CUDA_TRY(cudaMemcpyAsync(ctx->d_ref_code.p, codes.data(), n, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->table_dirty = true;
-  ctx->staged = false;
   return SWB_OK;
 }
 
@@ -1014,12 +1058,12 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
   std::map<uint32_t, std::vector<std::pair<int64_t, int64_t>>> ranges_by_m;
   uint64_t cells_ref = 0;
   size_t max_n = 0;
-  uint32_t max_m = 0;
+  uint32_t max_m = 0, min_m = 0xFFFFFFFFu;
   for (size_t r = 0; r < n_seqs; ++r) {
     const uint64_t m64 = offsets[r + 1] - offsets[r];
     if (m64 == 0) return fail(ctx, SWB_ERR_ARG, "empty sequence at index " + std::to_string(r));
     const uint32_t m = (uint32_t)m64, xo = (uint32_t)(offsets[r] - offsets[0]);
-    max_m = std::max(max_m, m);
+    max_m = std::max(max_m, m); min_m = std::min(min_m, m);
     cells_ref += (uint64_t)m * N;
     if (!chunked) { seeds.push_back({(uint32_t)r, 0u, 0u, (uint32_t)N, m, xo}); max_n = N; continue; }
     auto it = ranges_by_m.find(m);
@@ -1055,8 +1099,14 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     // warp per SM sub-partition is latency bound and two columns per step amortise the per-step latency
     // (few long pairs), and for batches too small to put more than one warp on an SM sub-partition
     ctx->C = (!ctx->force_l32 && (((seeds.size() + 1) / 2 < 148 * 8 && max_m > 1024) || (seeds.size() + 1) / 2 <= 148 * 4)) ? 2 : 1;
+    // four columns per step for the pipelined strips of few long pairs (score_units_kernel; instantiated for R <= 8):
+    // every sequence must span several strips, so that no other kernel sees the batch
+    bool few_long = false;
+    const int r_long = strip_rows(ctx, max_m, (uint32_t)max_n, (seeds.size() + 1) / 2, use_profile(ctx, false), &few_long);
+    const bool c4_ok = !ctx->force_l32 && few_long && r_long <= 8 && min_m > (uint32_t)(32 * r_long) && !getenv("SWB_NO_PIPELINE");
+    if (c4_ok) ctx->C = 4;
     if (ctx->force_l32) ctx->C = 1;
-    else if (const char* e = getenv("SWB_COLS")) ctx->C = atoi(e) == 2 ? 2 : 1;
+    else if (const char* e = getenv("SWB_COLS")) { const int c = atoi(e); ctx->C = (c == 4 && c4_ok) ? 4 : (c >= 2 ? 2 : 1); }
     while (B < 65536 && words_per_block * 4.0 * ((double)max_n / ((double)B * ctx->C) + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
     // SWB_FORCE_B: run small test batches with the checkpoint period a large batch would get (parity of the timed geometry)
     if (const char* e = getenv("SWB_FORCE_B")) B = std::max(32, std::min(65536, 1 << ilog2(atoi(e))));

@@ -108,6 +108,35 @@ def mutated_reads_fast(ref_u8, count, read_len, seed, sub=0.01):
     return np.ascontiguousarray(reads)
 
 
+def mutated_reads_vec(ref_u8, count, read_len, seed, sub=0.01, ins=0.001, dele=0.001):
+    """Vectorised read sampler WITH indels for the 10^5..10^6-read batches bench.py times: (count, read_len) uint8.
+
+    Same error model as mutated_reads (py/ompfg_data_prep.py:98-104 samples windows; the 1 % / 0.1 % / 0.1 % rates are
+    SURVEY §8d's C3 workload): a window of the reference is walked base by base; a base is dropped with probability
+    `dele`, otherwise emitted (substituted with probability `sub`) and followed, with probability `ins`, by one random
+    base; the first read_len emitted symbols are the read."""
+    rng = np.random.default_rng(seed)
+    n = len(ref_u8)
+    slack = max(8, int(read_len * (ins + dele) * 8) + 8)
+    w = read_len + slack
+    starts = rng.integers(0, n - w + 1, size=count)
+    src = ref_u8[starts[:, None] + np.arange(w)[None, :]]
+    subm = rng.random(src.shape) < sub
+    src[subm] = DNA[rng.integers(0, 4, size=int(subm.sum()))]
+    keep = rng.random(src.shape) >= dele
+    insm = keep & (rng.random(src.shape) < ins)
+    emitted = keep.astype(np.int32) + insm.astype(np.int32)          # symbols this source position contributes
+    first = np.cumsum(emitted, axis=1) - emitted                     # output index of its first symbol
+    out = np.zeros((count, read_len), dtype=np.uint8)
+    rows = np.broadcast_to(np.arange(count)[:, None], src.shape)
+    sel = keep & (first < read_len)
+    out[rows[sel], first[sel]] = src[sel]
+    sel = insm & (first + 1 < read_len)
+    out[rows[sel], first[sel] + 1] = DNA[rng.integers(0, 4, size=int(sel.sum()))]
+    assert (out != 0).all()
+    return out
+
+
 def c3_reads(ref, count, read_len=150, seed=23):
     return mutated_reads(ref, count, read_len, seed, sub=0.01, ins=0.001, dele=0.001)
 
