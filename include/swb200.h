@@ -47,6 +47,7 @@ typedef struct swb_ctx swb_ctx;
 /* Per-alignment result flags (out_flags) */
 #define SWB_RES_CONS_TRUNCATED 1u /* consensus longer than cons_stride: strings truncated, score/end still exact */
 
+int swb_device_count(void); /* CUDA devices visible to this process (0 when there is none) */
 int swb_create(int device, swb_ctx** out);
 void swb_destroy(swb_ctx* ctx);
 const char* swb_last_error(const swb_ctx* ctx);

@@ -20,7 +20,7 @@ FLAG_CONSENSUS = 1
 ERR_NAMES = {-1: "SWB_ERR_CUDA", -2: "SWB_ERR_ARG", -3: "SWB_ERR_RANGE", -4: "SWB_ERR_SCORING", -5: "SWB_ERR_UNSUPPORTED", -6: "SWB_ERR_STATE"}
 
 # every symbol include/swb200.h declares
-EXPORTS = ["swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_set_scoring", "swb_set_scoring_match",
+EXPORTS = ["swb_device_count", "swb_create", "swb_destroy", "swb_last_error", "swb_version", "swb_set_scoring", "swb_set_scoring_match",
            "swb_set_reference", "swb_align_batch", "swb_batch_stage", "swb_batch_run", "swb_batch_fetch",
            "swb_batch_device_results", "swb_batch_rebind_reference", "swb_last_stats", "swb_make_string_range", "swb_matrix"]
 

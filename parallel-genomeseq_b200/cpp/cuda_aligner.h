@@ -29,6 +29,7 @@
 // getTimings()[0] is the time spent computing the matrix in microseconds — here DEVICE time from CUDA events.
 // Errors: the reference has none in-band (it asserts/aborts); the shims throw swb::Error.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +38,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -103,6 +105,8 @@ using ScoringFn = std::function<float(const char&, const char&)>;
 class Context {
  public:
   static Context& instance() { static thread_local Context c; return c; }
+  // device of this thread's context (before its first use); default: SWB_DEVICE or 0
+  void set_device(int dev) { if (!ctx_) device_ = dev; else if (dev != device_) throw Error(SWB_ERR_STATE, "Context::set_device after first use"); }
   swb_ctx* raw() { ensure(); return ctx_; }
   void check(int rc) { if (rc != SWB_OK) throw Error(rc, swb_last_error(ctx_)); }
 
@@ -145,12 +149,14 @@ class Context {
   std::vector<struct Pending*> pending_;
   void ensure() {
     if (ctx_) return;
-    int dev = 0;
-    if (const char* e = std::getenv("SWB_DEVICE")) dev = std::atoi(e);
+    int dev = device_;
+    if (dev < 0) { dev = 0; if (const char* e = std::getenv("SWB_DEVICE")) dev = std::atoi(e); }
+    device_ = dev;
     int rc = swb_create(dev, &ctx_);
     if (rc != SWB_OK) throw Error(rc, "swb_create failed: no usable CUDA device (libswb200 has no CPU fallback)");
   }
   swb_ctx* ctx_ = nullptr;
+  int device_ = -1;
   std::string ref_;
   bool have_match_ = false;
   int mode_ = -1;
@@ -386,6 +392,94 @@ class CUDABatchAligner {
   }
  private:
   int mode_;
+  detail::Scoring sc_;
+  std::string_view y_;
+};
+
+// The same batch over several GPUs of one box behind the C ABI: one host thread and one swb_ctx per device, the batch
+// partitioned over the devices, results merged on the host in input order.  This is the decomposition of the reference's
+// MPI drivers — reads / database files divided over worker ranks, results funnelled to one writer
+// (mpi_sw_solve_small.cpp:52-55,109-143; mpi_sw_solve_uniprot.cpp:65-72,95-138) — with host threads for ranks and no
+// message passing: alignments are independent and the drivers end in a CSV.
+class CUDAMultiGpuBatchAligner {
+ public:
+  enum Partition { BLOCK, BALANCED };   // BLOCK: contiguous floor(n / g) per device, the last takes the remainder
+                                        // (mpi_sw_solve_small.cpp:52-55); BALANCED: by residues, longest first to the
+                                        // least loaded device (ragged protein databases)
+  CUDAMultiGpuBatchAligner(int mode, int n_gpus) : mode_(mode) {
+    const int have = swb_device_count();
+    if (have <= 0) throw Error(SWB_ERR_CUDA, "no CUDA device (libswb200 has no CPU fallback)");
+    n_gpus_ = n_gpus <= 0 ? have : n_gpus;
+    if (n_gpus_ > have) throw Error(SWB_ERR_ARG, "more GPUs requested than visible");
+  }
+  int gpus() const { return n_gpus_; }
+  void set_scoring(float match, float mismatch, float gap) { sc_.is_fn = false; sc_.match = match; sc_.mismatch = mismatch; sc_.gap = gap; }
+  void set_scoring(ScoringFn fn, float gap) { sc_.is_fn = true; sc_.fn = std::move(fn); sc_.gap = gap; }
+  void set_reference(std::string_view y) { y_ = y; }
+
+  static std::vector<std::vector<size_t>> partition(const std::vector<std::string_view>& xs, int g, Partition how) {
+    std::vector<std::vector<size_t>> parts((size_t)g);
+    if (how == BLOCK) {
+      const size_t q = xs.size() / (size_t)g;
+      for (int r = 0; r < g; ++r) for (size_t i = (size_t)r * q; i < (r + 1 == g ? xs.size() : (size_t)(r + 1) * q); ++i) parts[(size_t)r].push_back(i);
+      return parts;
+    }
+    std::vector<size_t> order(xs.size());
+    for (size_t i = 0; i < xs.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return xs[a].size() > xs[b].size(); });
+    std::vector<unsigned long long> load((size_t)g, 0ull);
+    for (size_t i : order) {
+      size_t r = 0;
+      for (size_t k = 1; k < (size_t)g; ++k) if (load[k] < load[r]) r = k;
+      parts[r].push_back(i); load[r] += xs[i].size();
+    }
+    for (auto& p : parts) std::sort(p.begin(), p.end());
+    return parts;
+  }
+
+  CUDABatchAligner::Out align(const std::vector<std::string_view>& xs, int npiece = 0, float ratio = 0.f, bool consensus = true, Partition how = BLOCK) {
+    const auto parts = partition(xs, n_gpus_, how);
+    size_t maxlen = 0;
+    for (auto& x : xs) maxlen = std::max(maxlen, x.size());
+    CUDABatchAligner::Out o;
+    o.stride = consensus ? 2 * maxlen + 64 : 0;
+    o.score.resize(xs.size()); o.pos.resize(xs.size()); o.len.resize(xs.size()); o.flags.resize(xs.size());
+    if (consensus) { o.cx.resize(xs.size() * o.stride); o.cy.resize(xs.size() * o.stride); }
+    std::vector<float> dev_us((size_t)n_gpus_, 0.f);
+    std::vector<std::string> errors((size_t)n_gpus_);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_gpus_; ++r)
+      th.emplace_back([&, r]() {
+        try {
+          const auto& idx = parts[(size_t)r];
+          if (idx.empty()) return;
+          Context::instance().set_device(r);
+          CUDABatchAligner ba(mode_);
+          if (sc_.is_fn) ba.set_scoring(sc_.fn, sc_.gap); else ba.set_scoring(sc_.match, sc_.mismatch, sc_.gap);
+          ba.set_reference(y_);
+          std::vector<std::string_view> mine;
+          for (size_t i : idx) mine.push_back(xs[i]);
+          CUDABatchAligner::Out part = ba.align(mine, npiece, ratio, consensus);
+          for (size_t k = 0; k < idx.size(); ++k) {
+            const size_t i = idx[k];
+            o.score[i] = part.score[k]; o.pos[i] = part.pos[k]; o.len[i] = part.len[k]; o.flags[i] = part.flags[k];
+            if (consensus) {
+              const size_t nb = std::min<size_t>(part.len[k], std::min(part.stride, o.stride));
+              std::memcpy(o.cx.data() + i * o.stride, part.cx.data() + k * part.stride, nb);
+              std::memcpy(o.cy.data() + i * o.stride, part.cy.data() + k * part.stride, nb);
+            }
+          }
+          dev_us[(size_t)r] = part.device_us;
+        } catch (const std::exception& e) { errors[(size_t)r] = e.what(); }
+      });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n_gpus_; ++r) if (!errors[(size_t)r].empty()) throw Error(SWB_ERR_CUDA, "GPU " + std::to_string(r) + ": " + errors[(size_t)r]);
+    o.device_us = *std::max_element(dev_us.begin(), dev_us.end());   // the devices run concurrently
+    return o;
+  }
+
+ private:
+  int mode_, n_gpus_ = 1;
   detail::Scoring sc_;
   std::string_view y_;
 };

@@ -872,6 +872,11 @@ extern "C" {
 
 const char* swb_version(void) { return "swb200 0.1 (sm_100a)"; }
 
+int swb_device_count(void) {
+  int ndev = 0;
+  return cudaGetDeviceCount(&ndev) == cudaSuccess ? ndev : 0;
+}
+
 int swb_create(int device, swb_ctx** out) {
   if (!out) return SWB_ERR_ARG;
   *out = nullptr;

@@ -6,8 +6,9 @@
 // rank, which prints "read,pos_pred,score" rows ("%.126s" of the protein, :132; header :151-156).
 // Here: the database is ONE multi-FASTA file (the 561 356 one-protein files become one blob +
 // offsets), all proteins go through ONE batched call, and the same CSV is written by the same process.
-// Several GPUs: run one process per GPU on a contiguous block of the database (sharding.block_partition).
-//   sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M]
+// Several GPUs (--gpus G, 0 = all): the database is partitioned by residues over G GPUs, one host thread each, and the
+// rows are written in database order (mpi_sw_solve_uniprot.cpp:65-72 gives every rank a block of files).
+//   sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M] [--gpus G]
 //     default scoring = the reference's (a == b ? 3 : -3, gap 2); --blosum62 10 tabulates BLOSUM62 through the
 //     callback constructor surface (smithwaterman.h:16-17) with linear gap 10.
 #include <cstdio>
@@ -52,11 +53,12 @@ static bool read_fasta_records(const std::string& path, std::vector<std::string>
 
 int main(int argc, char** argv) {
   std::vector<std::string> pos;
-  bool blosum = false; float gap = 2.f; size_t first = 0, count = (size_t)-1;
+  bool blosum = false; float gap = 2.f; size_t first = 0, count = (size_t)-1; int gpus = 1;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--blosum62") && i + 1 < argc) { blosum = true; gap = (float)std::atof(argv[++i]); }
     else if (!std::strcmp(argv[i], "--first") && i + 1 < argc) first = (size_t)std::atoll(argv[++i]);
     else if (!std::strcmp(argv[i], "--count") && i + 1 < argc) count = (size_t)std::atoll(argv[++i]);
+    else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
     else pos.push_back(argv[i]);
   }
   if (pos.size() < 3) { std::cerr << "usage: sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M]" << std::endl; return 2; }
@@ -69,20 +71,26 @@ int main(int argc, char** argv) {
   std::vector<std::string_view> xs;
   for (size_t i = first; i < first + count; ++i) xs.emplace_back(db[i]);
 
-  swb::CUDABatchAligner aligner(SWB_MODE_EXACT);
-  aligner.set_reference(fa_string);
-  if (blosum) {
-    aligner.set_scoring([](const char& a, const char& b) -> float {
-      const char* pa = std::strchr(kOrder, a); const char* pb = std::strchr(kOrder, b);
-      if (!pa || !pb || !a || !b) return -4.f;
-      return (float)kBlosum62[pa - kOrder][pb - kOrder];
-    }, gap);
-  } else {
-    aligner.set_scoring(3.f, -3.f, 2.f);
-  }
+  auto blosum_fn = [](const char& a, const char& b) -> float {
+    const char* pa = std::strchr(kOrder, a); const char* pb = std::strchr(kOrder, b);
+    if (!pa || !pb || !a || !b) return -4.f;
+    return (float)kBlosum62[pa - kOrder][pb - kOrder];
+  };
   swb::CUDABatchAligner::Out out;
-  try { out = aligner.align(xs, 0, 0.f, /*consensus=*/false); }
-  catch (const swb::Error& e) { std::cerr << "search failed: " << e.what() << std::endl; return 1; }
+  try {
+    if (gpus == 1) {
+      swb::CUDABatchAligner aligner(SWB_MODE_EXACT);
+      aligner.set_reference(fa_string);
+      if (blosum) aligner.set_scoring(blosum_fn, gap); else aligner.set_scoring(3.f, -3.f, 2.f);
+      out = aligner.align(xs, 0, 0.f, /*consensus=*/false);
+    } else {
+      swb::CUDAMultiGpuBatchAligner aligner(SWB_MODE_EXACT, gpus);
+      aligner.set_reference(fa_string);
+      if (blosum) aligner.set_scoring(blosum_fn, gap); else aligner.set_scoring(3.f, -3.f, 2.f);
+      out = aligner.align(xs, 0, 0.f, /*consensus=*/false, swb::CUDAMultiGpuBatchAligner::BALANCED);
+      std::cout << "database partitioned by residues over " << aligner.gpus() << " GPUs" << std::endl;
+    }
+  } catch (const swb::Error& e) { std::cerr << "search failed: " << e.what() << std::endl; return 1; }
 
   std::ofstream csv(pos[2]);
   csv << "read,pos_pred,score\n";

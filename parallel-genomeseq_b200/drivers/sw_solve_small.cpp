@@ -6,9 +6,10 @@
 //   * output: header + ",pos_pred,score", rows "<input line>, <pos_pred>, <score>"  (:72-74,91-93)
 //   * "Average SW iter_ad_read times: <us>us, GCUP:<gcups>" with cells = sum len(read)*len(ref) (:88-89,102-106)
 // Difference: the per-read loop "construct aligner -> calculateScore -> getPos" becomes ONE batched call.
-//   sw_solve_small [fa] [reads.csv] [out.csv] [--npiece N --ratio R] [--float]
+//   sw_solve_small [fa] [reads.csv] [out.csv] [--npiece N --ratio R] [--float] [--gpus G]
 //     --npiece 17 --ratio 2.0 reproduces the reference's -DUSEOMP build (OMPParallelLocalAligner, :82);
-//     --float selects Similarity_Matrix (EXACT) arithmetic instead of Similarity_Matrix_Skewed (SAT_U8).
+//     --float selects Similarity_Matrix (EXACT) arithmetic instead of Similarity_Matrix_Skewed (SAT_U8);
+//     --gpus G divides the reads over G GPUs (0 = all) like mpi_sw_solve_small.cpp:52-55 divides them over ranks.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,12 +24,13 @@ int main(int argc, char** argv) {
   std::string fa_file_path = "data/data_small/genome.chr22.5K.fa";
   std::string input_file_path = "data/data_small_ground_truth.csv";
   std::string output_file_path = "data/align_output.csv";
-  int npiece = 0; float ratio = 2.0f; int mode = SWB_MODE_SAT_U8;
+  int npiece = 0; float ratio = 2.0f; int mode = SWB_MODE_SAT_U8; int gpus = 1;
   std::vector<std::string> pos;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--npiece") && i + 1 < argc) npiece = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--ratio") && i + 1 < argc) ratio = (float)std::atof(argv[++i]);
     else if (!std::strcmp(argv[i], "--float")) mode = SWB_MODE_EXACT;
+    else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
     else pos.push_back(argv[i]);
   }
   if (pos.size() > 0) fa_file_path = pos[0];
@@ -55,11 +57,19 @@ int main(int argc, char** argv) {
   }
   std::vector<std::string_view> views(reads.begin(), reads.end());
 
-  swb::CUDABatchAligner aligner(mode);
-  aligner.set_reference(fa_string);
   swb::CUDABatchAligner::Out out;
-  try { out = aligner.align(views, npiece, ratio, /*consensus=*/false); }
-  catch (const swb::Error& e) { std::cerr << "alignment failed: " << e.what() << std::endl; return 1; }
+  try {
+    if (gpus == 1) {
+      swb::CUDABatchAligner aligner(mode);
+      aligner.set_reference(fa_string);
+      out = aligner.align(views, npiece, ratio, /*consensus=*/false);
+    } else {
+      swb::CUDAMultiGpuBatchAligner aligner(mode, gpus);
+      aligner.set_reference(fa_string);
+      out = aligner.align(views, npiece, ratio, /*consensus=*/false, swb::CUDAMultiGpuBatchAligner::BLOCK);
+      std::cout << "reads divided over " << aligner.gpus() << " GPUs" << std::endl;
+    }
+  } catch (const swb::Error& e) { std::cerr << "alignment failed: " << e.what() << std::endl; return 1; }
 
   std::ofstream align_output(output_file_path);
   align_output << header << ",pos_pred,score\n";

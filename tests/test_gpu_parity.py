@@ -157,9 +157,9 @@ def test_cpp_shims_and_driver(tmp_path, data_small):
     exe = os.path.join(ROOT, "tests", "cpp", "test_shim")
     if not os.path.isfile(exe):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
-                               "-L", os.path.join(ROOT, "parallel-genomeseq_b200"), "-lswb200", "-Wl,-rpath," + os.path.join(ROOT, "parallel-genomeseq_b200")])
+                               "-L", os.path.join(ROOT, "parallel-genomeseq_b200"), "-lswb200", "-lpthread", "-Wl,-rpath," + os.path.join(ROOT, "parallel-genomeseq_b200")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "SHIM OK" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "SHIM OK" in out.stdout and "LAZY n=600" in out.stdout and "MULTI-GPU OK" in out.stdout, out.stdout + out.stderr
     drv = os.path.join(ROOT, "parallel-genomeseq_b200", "drivers", "sw_solve_small")
     if not os.path.isfile(drv):
         subprocess.check_call(["make", "-C", os.path.dirname(drv)])
@@ -584,3 +584,84 @@ def test_c5_full_size(engine, pkg):
                    hashlib.sha256(r["cx"][i].encode()).hexdigest(), hashlib.sha256(r["cy"][i].encode()).hexdigest())
             assert got == (e["score"], e["pos"], e["end"], e["len"], e["cx_sha256"], e["cy_sha256"]), (key, i, got[:4], e["score"], e["pos"], e["end"], e["len"])
             assert r["flags"][i] == 0
+
+
+def test_reference_unit_test_with_type_swap():
+    """The reference's OWN test/test_localaligner.cpp (score 13, pos 2, consensus CAGTTG / CA-TTG), compiled unmodified
+    against the reference headers and its vendored googletest with only the aligner type swapped to the CUDA shims
+    (-DSWB_WITH_REFERENCE_HEADERS, the mode INTEGRATION.md tells maintainers to use).  The binary is built in the build
+    container (tests/cpp/build_ref_tests.py needs /root/reference) and travels with the snapshot."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "cpp", "ref_test_localaligner")
+    if not os.path.isfile(exe):
+        if not os.path.isdir("/root/reference"):
+            pytest.skip("ref_test_localaligner was not built (needs /root/reference at build time)")
+        subprocess.check_call([os.sys.executable, os.path.join(ROOT, "tests", "cpp", "build_ref_tests.py")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "[  PASSED  ] 2 tests" in r.stdout, r.stdout + r.stderr
+
+
+def test_drivers_over_several_gpus(tmp_path, data_small, c4_sample):
+    """--gpus N of the batched drivers (one host thread + one context per device behind the C ABI, reads block-
+    partitioned like mpi_sw_solve_small.cpp:52-55, database partitioned by residues): same CSV as the goldens.  Runs
+    with every device count the box has (1 on a single-GPU box: the threaded path with one worker)."""
+    import os
+    import subprocess
+    from conftest import ROOT, GOLDEN
+    ddir = os.path.join(ROOT, "parallel-genomeseq_b200", "drivers")
+    import torch
+    ndev = torch.cuda.device_count()
+    want = read_golden_csv("data_small_sw_skewed.csv")
+    for g in sorted({0, min(2, ndev), ndev}):
+        csv_out = str(tmp_path / f"align_{g}.csv")
+        r = subprocess.run([os.path.join(ddir, "sw_solve_small"), os.path.join(GOLDEN, "data_small", "genome.chr22.5K.fa"), os.path.join(GOLDEN, "data_small", "data_small_ground_truth.csv"), csv_out, "--gpus", str(g)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "GCUP:" in r.stdout and (g == 1 or "reads divided over" in r.stdout), r.stdout + r.stderr
+        rows = open(csv_out).read().strip().split("\n")
+        assert len(rows) == 1171
+        for line, gd in zip(rows[1:], want):
+            f_ = line.split(", ")
+            assert int(f_[-2]) == gd["pos"] and float(f_[-1]) == gd["score"]
+    q = tmp_path / "query.fasta"
+    q.write_text(">query\n" + c4_sample["query"] + "\n")
+    db = tmp_path / "db.fasta"
+    with open(db, "w") as f:
+        for k, e in enumerate(c4_sample["entries"]):
+            f.write(f">sp|P{k:05d}|synthetic\n" + e["x"] + "\n")
+    out_csv = tmp_path / "out.csv"
+    r = subprocess.run([os.path.join(ddir, "sw_search_uniprot"), str(q), str(db), str(out_csv), "--blosum62", str(c4_sample["gap"]), "--gpus", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "partitioned by residues over" in r.stdout, r.stdout + r.stderr
+    rows = out_csv.read_text().strip().split("\n")
+    for line, e in zip(rows[1:], c4_sample["entries"]):
+        f_ = line.split(", ")
+        assert int(f_[1]) == e["pos"] and float(f_[2]) == e["score"]
+
+
+def test_rebind_reference_keeps_the_database_resident(engine, pkg):
+    """swb_batch_rebind_reference: many queries against one staged database (query-stationary mode); every query's result
+    equals a fresh stage, and a batch that is not in that mode refuses."""
+    db = synth.c4_database(3000, seed=9)
+    qs = synth.c4_queries(3, 300, seed=10) + synth.c4_queries(1, 250, seed=11)
+    t = synth.blosum62_table()
+    engine.set_scoring_table(pkg.MODE_EXACT, t, 10)
+    engine.set_reference(qs[0])
+    engine.stage(db, consensus=False)
+    for q in qs:
+        engine.rebind_reference(q)
+        engine.run()
+        r = engine.fetch()
+        for i in range(0, len(db), 97):
+            w = o.align(db[i], q, mode=o.MODE_EXACT, table=t, gap=10)
+            if w["score"] == 0:
+                assert int(r["score"][i]) == 0
+                continue
+            assert (int(r["score"][i]), int(r["pos"][i]), tuple(int(v) for v in r["end"][i])) == (w["score"], w["pos"], tuple(w["end"])), (len(q), i)
+        assert engine.stats()["cells_reference"] == sum(len(p) for p in db) * len(q)
+    engine.set_scoring_match(pkg.MODE_SAT_U8, 3, -3, 2)
+    engine.set_reference("ACGT" * 300)
+    engine.stage(["ACGTACGTTT" * 10] * 4)
+    with pytest.raises(pkg.SwbError) as ei:
+        engine.rebind_reference("ACGT" * 100)
+    assert ei.value.code == -6

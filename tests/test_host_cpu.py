@@ -199,3 +199,22 @@ def test_bench_peaks_and_metric_contract():
     with open(os.path.join(ROOT, "BASELINE.json")) as f:
         assert b.METRIC == json.load(f)["metric"]
     assert b.OPS_PER_CELL["SAT_U8"] == 9 and b.OPS_PER_CELL["EXACT"] == 8
+
+
+def test_sass_counts_match_the_build():
+    """profiles/sass_counts_r02.json (the instruction counts bench.py's issue-based roofline fraction uses) is what
+    tools/sass_counts.py computes from the objects of the current build."""
+    import shutil
+    if not shutil.which("cuobjdump") or not os.path.isfile(os.path.join(ROOT, "parallel-genomeseq_b200", "build", "sw_inst_r19.o")):
+        pytest.skip("needs cuobjdump and the build objects (build container)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_counts.py"), "--check"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_reference_headers_mode_compiles():
+    """cuda_aligner.h with -DSWB_WITH_REFERENCE_HEADERS against the reference's own headers, through the reference's
+    unit test file (tests/cpp/ref_test_swap.cpp); running it needs a GPU (tests/test_gpu_parity.py)."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference (build container)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpp", "build_ref_tests.py"), "--force"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and os.path.isfile(os.path.join(ROOT, "tests", "cpp", "ref_test_localaligner")), r.stdout + r.stderr
