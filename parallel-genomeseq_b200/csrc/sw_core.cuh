@@ -79,6 +79,7 @@ struct PassParams {
   uint32_t* progress;          // per unit: boundary columns published so far
   uint32_t* abort_flag;        // set when a consumer gave up waiting (never expected; avoids a hang)
   uint32_t* ticket;            // units are handed out in the order in which warps actually start (score_units_kernel)
+  int strips;                  // host: some pair of the class has more than one row strip (score_strips_kernel instead of score_kernel)
   int L, logL, B, logB;
   Scoring sc;
 };
@@ -92,7 +93,18 @@ __device__ __forceinline__ uint32_t hset2_eq(uint32_t a, uint32_t b) {
 }
 __device__ __forceinline__ uint32_t viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
 
-constexpr uint32_t NEG_INF2 = 0x80008000u;   // pack(-32768, -32768)
+constexpr uint32_t NEG_INF2 = 0x80008000u;   // pack(-32768, -32768); as one s32 (wide lanes) it is about -2^31: "minus infinity" for a max either way
+
+// Arithmetic of a lane register (template parameter AM of everything below):
+//   AM_EXACT  two s16 cells per register, no upper clamp          (Similarity_Matrix, scores < 2^15)
+//   AM_SAT    two s16 cells per register, clamped to [0, 255]     (Similarity_Matrix_Skewed)
+//   AM_WIDE   ONE s32 cell per register, no upper clamp           (Similarity_Matrix with scores >= 2^15: the reference's f32
+//             matrix is exact to 2^24, similaritymatrix.cpp:49-54; same instruction count as AM_EXACT, half the cells per
+//             instruction; only half A of a pair exists)
+constexpr int AM_EXACT = 0, AM_SAT = 1, AM_WIDE = 2;
+template <bool WIDE> __device__ __forceinline__ uint32_t lane_max(uint32_t a, uint32_t b) { return WIDE ? (uint32_t)max((int)a, (int)b) : __vmaxs2(a, b); }
+// value of one alignment's cell in a packed word: the task's half (s16) or the whole word (wide lanes)
+template <bool WIDE> __device__ __forceinline__ int lane_val(uint32_t v, uint32_t half) { return WIDE ? (int)v : (int)(int16_t)(half ? (v >> 16) : (v & 0xFFFFu)); }
 // Symbols are compared as fp16 bit patterns by HSET2; 0x4000 | byte is a NORMAL fp16 number (2.0 .. 2.5),
 // so the comparison never touches subnormals, signed zeros or NaNs.
 constexpr uint32_t SYM_BASE = 0x4000u;
@@ -115,20 +127,23 @@ struct LaneState {
 };
 // Checkpoint words per lane: E[R], up_prev, bot[0..C-2] = R + C registers.  In SAT_U8 mode every value is
 // E + G in [0, 255], so two registers (four bytes) share one word and the checkpoints take half the HBM.
-template <int R, int C, bool SAT> __host__ __device__ constexpr int state_words() { return SAT ? (R + C + 1) / 2 : R + C; }
+template <int R, int C, int AM> __host__ __device__ constexpr int state_words() { return AM == AM_SAT ? (R + C + 1) / 2 : R + C; }
 
 // Geometry of the skewed wavefront: at step t (1-based) lane g works on columns col_of(t,g,0..C-1).
 template <int C> __device__ __forceinline__ int col_of(int t, int g, int c) { return C * (t - g - 1) + 1 + c; }
 template <int C> __device__ __forceinline__ int step_of(int j, int g) { return g + (j + C - 1) / C; }
 
 // Symbol selection: returns pack(s+G) for row k against column c of the current step.
-template <int R, int C>
+template <int R, int C, bool WIDE = false>
 struct CompareSelect {
   uint32_t q[R];        // pack(symA[row], symB[row])
   uint32_t r2[C];       // pack(y[j_c], y[j_c])
   uint32_t sel_and, sel_xor;
   __device__ __forceinline__ void set_column(int c, uint32_t ysym) { r2[c] = ysym * 0x00010001u; }
-  __device__ __forceinline__ uint32_t operator()(int k, int c) const { return (hset2_eq(q[k], r2[c]) & sel_and) ^ sel_xor; }
+  __device__ __forceinline__ uint32_t operator()(int k, int c) const {
+    if (WIDE) return (((q[k] ^ r2[c]) & 0xFFFFu) == 0u ? sel_and : 0u) ^ sel_xor;      // half A only, one s32 score
+    return (hset2_eq(q[k], r2[c]) & sel_and) ^ sel_xor;
+  }
 };
 
 // Profile selection: per-warp query profile in shared memory, word index ((code*R + k)*32 + lane).
@@ -143,9 +158,10 @@ struct ProfileSelect {
 // One wavefront step for one lane: C columns of rows [g*R, (g+1)*R).  The C column chains are independent
 // up to a one-row skew, which is where the instruction-level parallelism comes from.
 //   hook(k, c, E_new): every new cell, E-space (H - G), packed s16x2.
-template <int R, int C, bool SAT, class Select, class Hook>
+template <int R, int C, int AM, class Select, class Hook>
 __device__ __forceinline__ void step(LaneState<R, C>& st, const Select& sel, const Scoring& sc, const uint32_t (&upv)[C],
                                      uint32_t& bmax, Hook&& hook) {
+  constexpr bool SAT = AM == AM_SAT, WIDE = AM == AM_WIDE;
   uint32_t above[C + 1];          // row k-1: [0] = last column of the previous step, [c+1] = column c of this step
   above[0] = st.up_prev;
 #pragma unroll
@@ -157,17 +173,22 @@ __device__ __forceinline__ void step(LaneState<R, C>& st, const Select& sel, con
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const uint32_t sG = sel(k, c);
-      const uint32_t d = __viaddmax_s16x2_relu(above[c], sG, cur[c]);                  // max(NW + s, W - G, 0)
-      const uint32_t dG = SAT ? viaddmin_s16x2(d, sc.negG2, sc.ceil2) : __vadd2(d, sc.negG2);   // min(., 255) - G
-      cur[c + 1] = __viaddmax_s16x2(above[c + 1], sc.negG2, dG);                       // max(N - G, .) = H - G
+      if (WIDE) {                                                                       // the same three operations on one s32 cell
+        const int d = __viaddmax_s32_relu((int)above[c], (int)sG, (int)cur[c]);
+        cur[c + 1] = (uint32_t)__viaddmax_s32((int)above[c + 1], (int)sc.negG2, d + (int)sc.negG2);
+      } else {
+        const uint32_t d = __viaddmax_s16x2_relu(above[c], sG, cur[c]);                  // max(NW + s, W - G, 0)
+        const uint32_t dG = SAT ? viaddmin_s16x2(d, sc.negG2, sc.ceil2) : __vadd2(d, sc.negG2);   // min(., 255) - G
+        cur[c + 1] = __viaddmax_s16x2(above[c + 1], sc.negG2, dG);                       // max(N - G, .) = H - G
+      }
       hook(k, c, cur[c + 1]);
     }
     if (C % 2 == 0) {
 #pragma unroll
-      for (int c = 0; c < C; c += 2) bmax = __vimax3_s16x2(bmax, cur[c + 1], cur[c + 2]);
+      for (int c = 0; c < C; c += 2) bmax = WIDE ? (uint32_t)__vimax3_s32((int)bmax, (int)cur[c + 1], (int)cur[c + 2]) : __vimax3_s16x2(bmax, cur[c + 1], cur[c + 2]);
     } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) bmax = __vmaxs2(bmax, cur[c + 1]);
+      for (int c = 0; c < C; ++c) bmax = lane_max<WIDE>(bmax, cur[c + 1]);
     }
     st.E[k] = cur[C];
 #pragma unroll
@@ -223,8 +244,9 @@ template <int R, int C>
 __device__ __forceinline__ uint32_t state_reg(const LaneState<R, C>& st, int i) {
   return i < R ? st.E[i] : (i == R ? st.up_prev : st.bot[i - R - 1]);
 }
-template <int R, int C, bool SAT>
+template <int R, int C, int AM>
 __device__ __forceinline__ void save_state(const LaneState<R, C>& st, const Scoring& sc, uint32_t* ck, int L, int g) {
+  constexpr bool SAT = AM == AM_SAT;
   constexpr int N = R + C;
   if (SAT) {
     const uint32_t g2 = (uint32_t)sc.G * 0x00010001u;   // pack(+G, +G): E + G is in [0, 255]
@@ -240,27 +262,27 @@ __device__ __forceinline__ void save_state(const LaneState<R, C>& st, const Scor
   }
 }
 // value of checkpoint register i (packed E word) from a checkpoint
-template <int R, int C, bool SAT>
+template <int R, int C, int AM>
 __device__ __forceinline__ uint32_t ck_reg(const Scoring& sc, const uint32_t* ck, int L, int g, int i) {
-  if (SAT) {
+  if (AM == AM_SAT) {
     const uint32_t w = ck[(i >> 1) * L + g];
     const uint32_t v = (i & 1) ? __byte_perm(w, 0u, 0x4342) : __byte_perm(w, 0u, 0x4140);   // two bytes -> two u16 halves
     return __vadd2(v, sc.negG2);
   }
   return ck[i * L + g];
 }
-template <int R, int C, bool SAT>
+template <int R, int C, int AM>
 __device__ __forceinline__ void load_state(LaneState<R, C>& st, const Scoring& sc, const uint32_t* ck, int L, int g) {
 #pragma unroll
-  for (int k = 0; k < R; ++k) st.E[k] = ck_reg<R, C, SAT>(sc, ck, L, g, k);
-  st.up_prev = ck_reg<R, C, SAT>(sc, ck, L, g, R);
+  for (int k = 0; k < R; ++k) st.E[k] = ck_reg<R, C, AM>(sc, ck, L, g, k);
+  st.up_prev = ck_reg<R, C, AM>(sc, ck, L, g, R);
 #pragma unroll
-  for (int c = 0; c < C - 1; ++c) st.bot[c] = ck_reg<R, C, SAT>(sc, ck, L, g, R + 1 + c);
+  for (int c = 0; c < C - 1; ++c) st.bot[c] = ck_reg<R, C, AM>(sc, ck, L, g, R + 1 + c);
   st.bot[C - 1] = st.E[R - 1];
 }
 
-template <int R, int C>
-__device__ __forceinline__ void load_compare_rows(CompareSelect<R, C>& sel, const PassParams& p, const PairDesc& pd, int g) {
+template <int R, int C, bool WIDE>
+__device__ __forceinline__ void load_compare_rows(CompareSelect<R, C, WIDE>& sel, const PassParams& p, const PairDesc& pd, int g) {
   const uint32_t* q = p.qpairs + pd.q_off + (uint32_t)g * R;
 #pragma unroll
   for (int k = 0; k < R; ++k) sel.q[k] = __ldg(q + k);
@@ -269,7 +291,7 @@ __device__ __forceinline__ void load_compare_rows(CompareSelect<R, C>& sel, cons
 }
 
 // Build this lane's slice of the per-warp profile: prof[(code*R + k)*32 + lane] = pack(T[xA][code], T[xB][code]).
-template <int R>
+template <int R, bool WIDE = false>
 __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassParams& p, const PairDesc& pd, int g, int lane) {
   const uint32_t* q = p.qpairs + pd.q_off + (uint32_t)g * R;
   for (int k = 0; k < R; ++k) {
@@ -279,14 +301,15 @@ __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassPar
       // sentinel rows (a/b >= 256) and the sentinel column use the table's last row/column: never a match
       const int16_t sa = p.table[(a < 256 ? a : 256) * p.KP + c];
       const int16_t sb = p.table[(b < 256 ? b : 256) * p.KP + c];
-      prof_warp[(c * R + k) * 32 + lane] = (uint32_t)(uint16_t)sa | ((uint32_t)(uint16_t)sb << 16);
+      prof_warp[(c * R + k) * 32 + lane] = WIDE ? (uint32_t)(int32_t)sa : ((uint32_t)(uint16_t)sa | ((uint32_t)(uint16_t)sb << 16));
     }
   }
 }
 
 // maximum of a packed s16x2 word over the L lanes of a group (all 32 lanes call it)
+template <bool WIDE = false>
 __device__ __forceinline__ uint32_t group_max_s16x2(uint32_t v, int L) {
-  for (int o = L >> 1; o > 0; o >>= 1) v = __vmaxs2(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = L >> 1; o > 0; o >>= 1) v = lane_max<WIDE>(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
@@ -297,10 +320,11 @@ __device__ __forceinline__ uint32_t group_max_s16x2(uint32_t v, int L) {
 // Strips run top to bottom; the last row of strip s is written to a boundary row in HBM (one packed word
 // per column) and read back as the "north" input of strip s+1 — 32 columns per coalesced load, handed to
 // lane 0 with one shuffle per step.  BND selects that code path (compiled out for single-strip launches).
-template <int R, int C, bool SAT, bool PROFILE>
+template <int R, int C, int AM, bool PROFILE>
 struct Wavefront {
+  static constexpr bool SAT = AM == AM_SAT, WIDE = AM == AM_WIDE;
   const PassParams& p;
-  CompareSelect<R, C> csel;
+  CompareSelect<R, C, WIDE> csel;
   ProfileSelect<R, C> psel;
   LaneState<R, C> st;
   int L, g, lane;
@@ -314,7 +338,7 @@ struct Wavefront {
   __device__ __forceinline__ Wavefront(const PassParams& p_) : p(p_) {}
 
   __device__ __forceinline__ size_t blk_index(const PairDesc& pd, int b) const { return (size_t)strip * pd.nblk + b; }
-  __device__ __forceinline__ size_t ck_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * state_words<R, C, SAT>() * L; }
+  __device__ __forceinline__ size_t ck_index(const PairDesc& pd, int b) const { return ((size_t)strip * pd.nblk + b) * state_words<R, C, AM>() * L; }
 
   // select the strip and load its rows (registers or shared-memory profile)
   __device__ __forceinline__ void prepare(const PairDesc& pd, int s, uint32_t* prof_warp) {
@@ -324,7 +348,7 @@ struct Wavefront {
     PairDesc sp = pd;
     sp.q_off = pd.q_off + (uint32_t)s * (uint32_t)(L * R);
     if (PROFILE) {
-      build_profile<R>(prof_warp, p, sp, g, lane);     // every lane fills (and later reads) only its own column
+      build_profile<R, WIDE>(prof_warp, p, sp, g, lane);     // every lane fills (and later reads) only its own column
       psel.prof = prof_warp + lane;
     } else {
       load_compare_rows<R, C>(csel, p, sp, g);
@@ -335,8 +359,8 @@ struct Wavefront {
   const uint32_t* restore_from = nullptr;
   __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
     if (t0 == 0) init_state<R, C>(st, p.sc);
-    else if (restore_from) load_state<R, C, SAT>(st, p.sc, restore_from, 32, lane);
-    else load_state<R, C, SAT>(st, p.sc, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
+    else if (restore_from) load_state<R, C, AM>(st, p.sc, restore_from, 32, lane);
+    else load_state<R, C, AM>(st, p.sc, p.ckpt + pd.ck_off + ck_index(pd, (t0 >> p.logB) - 1), L, g);
   }
   template <bool MASKED>
   __device__ __forceinline__ void load_symbols_m(const PairDesc& pd, int t, uint32_t (&y)[C]) const {
@@ -382,7 +406,7 @@ struct Wavefront {
         if (g == 0) upv[c] = p.sc.negG2;                  // row 0 of H is zero: E = -G
       }
     }
-    step<R, C, SAT>(st, sel, p.sc, upv, bmax, [&](int k, int c, uint32_t e_new) { hook(k, c, t, col_of<C>(t, g, c), e_new); });
+    step<R, C, AM>(st, sel, p.sc, upv, bmax, [&](int k, int c, uint32_t e_new) { hook(k, c, t, col_of<C>(t, g, c), e_new); });
     if (BND) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -497,8 +521,8 @@ struct Wavefront {
 // Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp (or one warp per strip).
 // Blocks whose columns (plus the two-step look-ahead) are inside [1, n] for every lane skip the range tests.
 // ======================================================================================================
-template <int R, int C, bool SAT, bool PROFILE, bool BND>
-__device__ __forceinline__ void score_pass(Wavefront<R, C, SAT, PROFILE>& wf, const PassParams& p, const PairDesc& pd,
+template <int R, int C, int AM, bool PROFILE, bool BND>
+__device__ __forceinline__ void score_pass(Wavefront<R, C, AM, PROFILE>& wf, const PassParams& p, const PairDesc& pd,
                                            int steps, int n_min, bool live) {
   const int L = wf.L, g = wf.g;
   uint32_t* blk = p.blkmax + pd.blk_off;
@@ -512,21 +536,27 @@ __device__ __forceinline__ void score_pass(Wavefront<R, C, SAT, PROFILE>& wf, co
     const bool interior = (t0 + 1 >= L) && ((t0 + p.B + 2) * C <= n_min);
     if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps<false, BND>(pd, t, bmax, nohook); }
     else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps<true, BND>(pd, t, bmax, nohook); }
-    const uint32_t gm = group_max_s16x2(bmax, L);
+    const uint32_t gm = group_max_s16x2<AM == AM_WIDE>(bmax, L);
     if (live && b < (int)pd.nblk) {
       if (g == 0) blk[wf.blk_index(pd, b)] = gm;
-      save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
+      save_state<R, C, AM>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
     }
     bmax = NEG_INF2;
   }
 }
 
+// Resident thread blocks per SM the score kernels are compiled for: 4 x 128 threads (16 warps) up to 19 rows per lane —
+// the register bound (<= 128) that keeps the hot loop at its measured occupancy whatever ptxas would otherwise pick
+// (round 2: an unrelated edit let it take 138 registers, 3 blocks per SM, 84 % instead of 88 % ALU-pipe busy).
 #ifndef SWB_SCORE_MINBLOCKS
-#define SWB_SCORE_MINBLOCKS 1
+#define SWB_SCORE_MINBLOCKS(R) ((R) <= 19 ? 4 : ((R) <= 24 ? 3 : 2))
 #endif
-template <int R, int C, bool SAT, bool PROFILE>
-__global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS) score_kernel(const PassParams p) {
-  extern __shared__ uint32_t smem_prof[];
+// The batched kernel exists twice: score_kernel for classes whose pairs all fit ONE strip (every read-mapping batch: the
+// hot kernel of the C3 benchmark) and score_strips_kernel for classes with row strips run top to bottom by one warp.
+// ptxas allocates registers and schedules per kernel, so keeping the strip loop out of score_kernel keeps its hot loop
+// independent of edits to the strip path (tools/sass_counts.py --check pins its instruction count).
+template <int R, int C, int AM, bool PROFILE, bool STRIPS>
+__device__ __forceinline__ void score_batched(const PassParams& p, uint32_t* smem_prof) {
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
@@ -539,26 +569,39 @@ __global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS) score_kernel(const P
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
   const PairDesc pd = p.pairs[pair];
 
-  Wavefront<R, C, SAT, PROFILE> wf(p);
+  Wavefront<R, C, AM, PROFILE> wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
 
   // run whole blocks so that every lane flushes together; lanes past their range see sentinel columns
   const int steps = warp_max_i32((int)pd.nblk << p.logB);
-  const int nstrips = warp_max_i32((int)pd.nstrips);    // > 1 only with L == 32 (one pair per warp)
   int n_min = (int)pd.n;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_min = min(n_min, __shfl_xor_sync(0xffffffffu, n_min, o));
-  if (nstrips > 1) {
+  if (STRIPS) {
+    const int nstrips = warp_max_i32((int)pd.nstrips);    // > 1 only with L == 32 (one pair per warp)
     for (int s = 0; s < nstrips; ++s) {
       wf.prepare(pd, s, prof_warp);
-      score_pass<R, C, SAT, PROFILE, true>(wf, p, pd, steps, n_min, live);
+      if (!live) wf.bnd_out = nullptr;   // a padding warp shadows the last pair: it must not write that pair's boundary rows again
+      score_pass<R, C, AM, PROFILE, true>(wf, p, pd, steps, n_min, live);
       __syncwarp();                       // boundary row of strip s is complete before strip s+1 reads it
       __threadfence_block();
     }
   } else {
     wf.prepare(pd, 0, prof_warp);
-    score_pass<R, C, SAT, PROFILE, false>(wf, p, pd, steps, n_min, live);
+    score_pass<R, C, AM, PROFILE, false>(wf, p, pd, steps, n_min, live);
   }
+}
+
+template <int R, int C, int AM, bool PROFILE>
+__global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS(R)) score_kernel(const PassParams p) {
+  extern __shared__ uint32_t smem_prof[];
+  score_batched<R, C, AM, PROFILE, false>(p, smem_prof);
+}
+
+template <int R, int C, int AM, bool PROFILE>
+__global__ void __launch_bounds__(128) score_strips_kernel(const PassParams p) {
+  extern __shared__ uint32_t smem_prof[];
+  score_batched<R, C, AM, PROFILE, true>(p, smem_prof);
 }
 
 // ======================================================================================================
@@ -573,9 +616,9 @@ __global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS) score_kernel(const P
 // to Wavefront::step_sel<true>: the boundary row is stored by a precomputed writer lane without range tests in
 // interior blocks, and progress is published once per few blocks instead of being tested per column.
 // ======================================================================================================
-template <int R, int C, bool SAT, bool PROFILE>
-struct UnitsWavefront : Wavefront<R, C, SAT, PROFILE> {
-  using Base = Wavefront<R, C, SAT, PROFILE>;
+template <int R, int C, int AM, bool PROFILE>
+struct UnitsWavefront : Wavefront<R, C, AM, PROFILE> {
+  using Base = Wavefront<R, C, AM, PROFILE>;
   bool writer = false;     // lane 31 of a strip that has a strip below it
   uint32_t chunk_next2 = 0;   // boundary chunks are fetched TWO chunks (64 columns) ahead of their use
   __device__ __forceinline__ UnitsWavefront(const PassParams& p_) : Base(p_) {}
@@ -591,7 +634,7 @@ struct UnitsWavefront : Wavefront<R, C, SAT, PROFILE> {
       const uint32_t north = __shfl_sync(0xffffffffu, this->chunk_cur, (base & 31) + c);
       if (this->lane == 0) upv[c] = north;
     }
-    step<R, C, SAT>(this->st, sel, this->p.sc, upv, bmax, [](int, int, uint32_t) {});
+    step<R, C, AM>(this->st, sel, this->p.sc, upv, bmax, [](int, int, uint32_t) {});
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = col_of<C>(t, this->lane, c);
@@ -628,7 +671,7 @@ struct UnitsWavefront : Wavefront<R, C, SAT, PROFILE> {
   }
 };
 
-template <int R, int C, bool SAT, bool PROFILE>
+template <int R, int C, int AM, bool PROFILE>
 __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
   const int lane = threadIdx.x & 31;
@@ -642,7 +685,7 @@ __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
   if (gwarp >= p.nunits) return;
   const uint2 u = p.units[gwarp];
   const PairDesc pd = p.pairs[u.x];
-  UnitsWavefront<R, C, SAT, PROFILE> wf(p);
+  UnitsWavefront<R, C, AM, PROFILE> wf(p);
   wf.L = 32; wf.g = lane; wf.lane = lane;
   wf.prepare(pd, (int)u.y, prof_warp);
   wf.writer = wf.bnd_out != nullptr && lane == 31;
@@ -664,9 +707,9 @@ __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
     const bool interior = (t0 + 1 >= 32) && ((t0 + p.B + 2) * C <= n);
     if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<false>(pd, t, bmax); }
     else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<true>(pd, t, bmax); }
-    const uint32_t gm = group_max_s16x2(bmax, 32);
+    const uint32_t gm = group_max_s16x2<AM == AM_WIDE>(bmax, 32);
     if (lane == 0) blk[wf.blk_index(pd, b)] = gm;
-    save_state<R, C, SAT>(wf.st, p.sc, ck + wf.ck_index(pd, b), 32, lane);
+    save_state<R, C, AM>(wf.st, p.sc, ck + wf.ck_index(pd, b), 32, lane);
     bmax = NEG_INF2;
     if (publish_to && (++since_pub >= pub_every || b == nb - 1)) {
       since_pub = 0;
@@ -748,8 +791,9 @@ __device__ __forceinline__ int group_max_i32(int v, int L) {
 #ifndef SWB_TRACE_MINBLOCKS
 #define SWB_TRACE_MINBLOCKS 4
 #endif
-template <int R, int C, bool SAT, bool PROFILE, bool QS, class WF>
+template <int R, int C, int AM, bool PROFILE, bool QS, class WF>
 __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem_prof, int qs_m) {
+  constexpr bool SAT = AM == AM_SAT, WIDE = AM == AM_WIDE;
   const PassParams& p = tp.pp;
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -790,8 +834,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
 
     // ---- 1. maximum over the block maxima (E-space) ------------------------------------------------------
     const uint32_t* blk = p.blkmax + pd.blk_off;
-    int vmax = -32768;
-    for (int w = g; w < nunits; w += L) vmax = max(vmax, half_of(blk[w], half));
+    int vmax = WIDE ? (int)NEG_INF2 : -32768;
+    for (int w = g; w < nunits; w += L) vmax = max(vmax, lane_val<WIDE>(blk[w], half));
     vmax = group_max_i32(vmax, L);
     const int score = vmax + G;
     if (tp.counters && lane == 0) { const long long tk1 = clock64(); atomicAdd(tp.counters + 9, (unsigned long long)(tk1 - tk0)); tk0 = tk1; }
@@ -813,8 +857,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
     const int row_min = (score + tp.max_pos - 1) / max(tp.max_pos, 1);   // a cell worth `score` cannot sit above this row
     uint64_t best = ~0ull;
     int cursor = active ? 0 : 2 * nunits;            // [0, nunits): phase 0, [nunits, 2*nunits): phase 1
-    const uint32_t vmax2 = (uint32_t)(uint16_t)(int16_t)vmax * 0x00010001u;
-    const uint32_t hmask = half ? 0xFFFF0000u : 0x0000FFFFu;
+    const uint32_t vmax2 = WIDE ? (uint32_t)vmax : (uint32_t)(uint16_t)(int16_t)vmax * 0x00010001u;
+    const uint32_t hmask = WIDE ? 0xFFFFFFFFu : (half ? 0xFFFF0000u : 0x0000FFFFu);
     while (true) {
       int myu = -1;
       while (true) {                                   // warp-uniform loop; the body is predicated per group
@@ -827,7 +871,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
           const int phase = pos >= nunits;
           u = pos - phase * nunits;
           const int us = u / nblk, ub = u - us * nblk;
-          if (half_of(blk[u], half) == vmax) {
+          if (lane_val<WIDE>(blk[u], half) == vmax) {
             const int t0 = ub << p.logB;
             const int jmin = max(1, C * (t0 - (L - 1)) + 1), jmax = min(n, C * (t0 + p.B));
             const int imin = max(us * S + 1, row_min), imax = min(m, (us + 1) * S);
@@ -914,10 +958,10 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
     // (left of the ring, above the band, or in the strip above); the next session starts there.  Every session also
     // saves the lane state every Wc steps into the warp's scratch (local checkpoints), so a follow-up session
     // restarts Wc..2*Wc steps back instead of at a pass-1 checkpoint up to B steps away.
-    constexpr int PW = SAT ? (R + 3) / 4 : (R + 1) / 2;       // packed ring words per lane and column
-    constexpr int EPW = SAT ? 4 : 2;                           // ring elements (cells) per word
+    constexpr int PW = SAT ? (R + 3) / 4 : (WIDE ? R : (R + 1) / 2);   // packed ring words per lane and column
+    constexpr int EPW = SAT ? 4 : (WIDE ? 1 : 2);              // ring elements (cells) per word
     constexpr int RP = PW * EPW;                               // element slots per lane: R rounded up to whole words
-    constexpr int SW = state_words<R, C, SAT>();
+    constexpr int SW = state_words<R, C, AM>();
     const int NB = tp.NB;
     const int cmask = tp.Wc * C - 1;                           // ring columns - 1 (Wc and C are powers of two)
     const int cstride = NB * PW;                               // words per ring column: the band's rows, lane by lane
@@ -970,6 +1014,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
                 const uint32_t b = 4 * w + 2 < R ? __byte_perm(v[4 * w + 2], 4 * w + 3 < R ? v[4 * w + 3] : 0u, sel2) : 0u;
                 dst[w] = __byte_perm(a, b, 0x5410);
               }
+            } else if (WIDE) {
+#pragma unroll
+              for (int w = 0; w < PW; ++w) dst[w] = v[w];       // wide lanes: the s32 cell itself
             } else {
 #pragma unroll
               for (int w = 0; w < PW; ++w)                      // two rows per word: the half's 16 bits
@@ -977,7 +1024,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
             }
           }
         }
-        if (on && (t & wmask) == 0) save_state<R, C, SAT>(wf.st, p.sc, lck + (size_t)((t >> tp.logWc) & (tp.nlc - 1)) * SW * 32, 32, lane);
+        if (on && (t & wmask) == 0) save_state<R, C, AM>(wf.st, p.sc, lck + (size_t)((t >> tp.logWc) & (tp.nlc - 1)) * SW * 32, 32, lane);
       });
       wf.restore_from = nullptr;
       if (!done) {
@@ -1007,13 +1054,14 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
           const int e = (RP == R) ? r : r + (r / R) * (RP - R);          // rows of a lane are padded to whole words
           const int col = ((j - 1) & cmask) * cstride;
           if (SAT) return (int)((reinterpret_cast<const uint8_t*>(ring)[col * 4 + e] + (uint32_t)G) & 0xFFu);
+          if (WIDE) return (int)ring[col + e] + G;
           return (int)reinterpret_cast<const int16_t*>(ring)[col * 2 + e] + G;
         };
         // any cell: the zero border, the boundary row of the strip above (HBM, packed E words), the ring, or -1 when
         // this session does not hold it
         auto cell = [&](int i, int j) -> int {
           if (i <= 0 || j <= 0) return 0;
-          if (i == row_lo) return half_of(__ldcg(above + j), half) + G;
+          if (i == row_lo) return lane_val<WIDE>(__ldcg(above + j), half) + G;
           if (i < i_min || j < j_min) return -1;
           return ring_val(i, j);
         };
@@ -1060,10 +1108,10 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
   }
 }
 
-template <int R, int C, bool SAT, bool PROFILE>
+template <int R, int C, int AM, bool PROFILE>
 __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) trace_kernel(const TraceParams tp) {
   extern __shared__ uint32_t smem_prof[];
-  trace_body<R, C, SAT, PROFILE, false, Wavefront<R, C, SAT, PROFILE>>(tp, smem_prof, 0);
+  trace_body<R, C, AM, PROFILE, false, Wavefront<R, C, AM, PROFILE>>(tp, smem_prof, 0);
 }
 
 // ======================================================================================================
@@ -1076,7 +1124,7 @@ struct DumpParams {
   int m, n;
 };
 
-template <int R, int C, bool SAT, bool PROFILE>
+template <int R, int C, int AM, bool PROFILE>
 __global__ void __launch_bounds__(128) dump_kernel(const DumpParams dp) {
   extern __shared__ uint32_t smem_prof[];
   const PassParams& p = dp.pp;
@@ -1085,7 +1133,7 @@ __global__ void __launch_bounds__(128) dump_kernel(const DumpParams dp) {
   const int L = p.L;                       // the host stages a single pair with L == 32
   const int g = lane & (L - 1);
   const PairDesc pd = p.pairs[0];
-  Wavefront<R, C, SAT, PROFILE> wf(p);
+  Wavefront<R, C, AM, PROFILE> wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
   const int S = L * R;
   const int steps = (int)pd.nblk << p.logB;
@@ -1095,7 +1143,7 @@ __global__ void __launch_bounds__(128) dump_kernel(const DumpParams dp) {
     const int row0 = s * S + g * R + 1;
     wf.replay(pd, multi, 0, steps, steps, [&](int k, int, int, int j, uint32_t e_new) {
       const int i = row0 + k;
-      if (i <= dp.m && j >= 1 && j <= dp.n) dp.out[(size_t)i * (dp.n + 1) + j] = half_of(e_new, 0) + p.sc.G;
+      if (i <= dp.m && j >= 1 && j <= dp.n) dp.out[(size_t)i * (dp.n + 1) + j] = lane_val<AM == AM_WIDE>(e_new, 0) + p.sc.G;
     });
     __syncwarp();
   }
@@ -1120,14 +1168,14 @@ __global__ void pack_rows_kernel(const uint8_t* reads_raw, const PairDesc* pairs
 
 // Per-task maximum (E-space + G = score) from the block maxima; used by the chunked path to pick the
 // best piece (plocalaligner.cpp:122-129) before any traceback.
-__global__ void task_max_kernel(const PairDesc* pairs, const TaskDesc* tasks, int ntasks, const uint32_t* blkmax, int G, int32_t* out) {
+__global__ void task_max_kernel(const PairDesc* pairs, const TaskDesc* tasks, int ntasks, const uint32_t* blkmax, int G, int wide, int32_t* out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntasks) return;
   const TaskDesc td = tasks[t];
   const PairDesc pd = pairs[td.pair];
   const uint32_t* blk = blkmax + pd.blk_off;
-  int v = -32768;
-  for (uint32_t w = 0; w < pd.nblk * pd.nstrips; ++w) v = max(v, half_of(blk[w], td.half));
+  int v = wide ? (int)NEG_INF2 : -32768;
+  for (uint32_t w = 0; w < pd.nblk * pd.nstrips; ++w) v = max(v, wide ? (int)blk[w] : half_of(blk[w], td.half));
   const int m = td.half ? pd.mB : pd.mA;
   out[t] = (m == 0) ? -1 : max(v + G, 0);
 }

@@ -21,53 +21,63 @@ cudaError_t go(K k, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P
   k<<<grid, block, smem, st>>>(p);
   return cudaGetLastError();
 }
-template <int C>
-cudaError_t score_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
-  if (profile) return sat ? go(score_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(score_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
-  return sat ? go(score_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(score_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
+// one instantiation per arithmetic mode (sw_core.cuh: AM_EXACT / AM_SAT / AM_WIDE) and symbol-score select
+template <int C, int AM>
+cudaError_t score_cm(bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  if (p.strips) return profile ? go(score_strips_kernel<SWB_R, C, AM, true>, grid, block, smem, st, p) : go(score_strips_kernel<SWB_R, C, AM, false>, grid, block, 0, st, p);
+  return profile ? go(score_kernel<SWB_R, C, AM, true>, grid, block, smem, st, p) : go(score_kernel<SWB_R, C, AM, false>, grid, block, 0, st, p);
 }
 template <int C>
-cudaError_t score_units_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
-  if (profile) return sat ? go(score_units_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(score_units_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
-  return sat ? go(score_units_kernel<SWB_R, C, true, false>, grid, block, 0, st, p) : go(score_units_kernel<SWB_R, C, false, false>, grid, block, 0, st, p);
+cudaError_t score_c(int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  return am == AM_SAT ? score_cm<C, AM_SAT>(profile, grid, block, smem, st, p) : am == AM_WIDE ? score_cm<C, AM_WIDE>(profile, grid, block, smem, st, p) : score_cm<C, AM_EXACT>(profile, grid, block, smem, st, p);
+}
+template <int C, int AM>
+cudaError_t score_units_cm(bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  return profile ? go(score_units_kernel<SWB_R, C, AM, true>, grid, block, smem, st, p) : go(score_units_kernel<SWB_R, C, AM, false>, grid, block, 0, st, p);
 }
 template <int C>
-cudaError_t trace_c(bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
-  if (profile) return sat ? go(trace_kernel<SWB_R, C, true, true>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, true>, grid, block, smem, st, p);
-  return sat ? go(trace_kernel<SWB_R, C, true, false>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, false, false>, grid, block, smem, st, p);   // smem: the pass-2 rings
+cudaError_t score_units_c(int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+  return am == AM_SAT ? score_units_cm<C, AM_SAT>(profile, grid, block, smem, st, p) : am == AM_WIDE ? score_units_cm<C, AM_WIDE>(profile, grid, block, smem, st, p) : score_units_cm<C, AM_EXACT>(profile, grid, block, smem, st, p);
+}
+template <int C, int AM>
+cudaError_t trace_cm(bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {   // smem: profiles + the pass-2 rings
+  return profile ? go(trace_kernel<SWB_R, C, AM, true>, grid, block, smem, st, p) : go(trace_kernel<SWB_R, C, AM, false>, grid, block, smem, st, p);
 }
 template <int C>
-cudaError_t dump_c(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
-  if (profile) return sat ? go(dump_kernel<SWB_R, C, true, true>, dim3(1), dim3(32), smem, st, p) : go(dump_kernel<SWB_R, C, false, true>, dim3(1), dim3(32), smem, st, p);
-  return sat ? go(dump_kernel<SWB_R, C, true, false>, dim3(1), dim3(32), 0, st, p) : go(dump_kernel<SWB_R, C, false, false>, dim3(1), dim3(32), 0, st, p);
+cudaError_t trace_c(int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+  return am == AM_SAT ? trace_cm<C, AM_SAT>(profile, grid, block, smem, st, p) : am == AM_WIDE ? trace_cm<C, AM_WIDE>(profile, grid, block, smem, st, p) : trace_cm<C, AM_EXACT>(profile, grid, block, smem, st, p);
+}
+template <int AM>
+cudaError_t dump_cm(bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
+  return profile ? go(dump_kernel<SWB_R, 1, AM, true>, dim3(1), dim3(32), smem, st, p) : go(dump_kernel<SWB_R, 1, AM, false>, dim3(1), dim3(32), 0, st, p);
 }
 }  // namespace
 
-cudaError_t SWB_CAT(swb_launch_dump_r, SWB_R)(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
-  return dump_c<1>(sat, profile, smem, st, p);
+cudaError_t SWB_CAT(swb_launch_dump_r, SWB_R)(int am, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
+  return am == AM_SAT ? dump_cm<AM_SAT>(profile, smem, st, p) : am == AM_WIDE ? dump_cm<AM_WIDE>(profile, smem, st, p) : dump_cm<AM_EXACT>(profile, smem, st, p);
 }
 // Four columns per step exist for the pipelined strips of few long pairs only (score_units_kernel and the pass-2 kernel
 // that replays its checkpoints), and only for thin strips.
 #if SWB_R <= 8
 #define SWB_HAVE_C4 1
 #endif
-cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
   if (p.units) {
 #ifdef SWB_HAVE_C4
-    if (C == 4) return score_units_c<4>(sat, profile, grid, block, smem, st, p);
+    if (C == 4) return score_units_c<4>(am, profile, grid, block, smem, st, p);
 #endif
     if (C > 2) return cudaErrorInvalidValue;
-    return C == 1 ? score_units_c<1>(sat, profile, grid, block, smem, st, p) : score_units_c<2>(sat, profile, grid, block, smem, st, p);
+    return C == 1 ? score_units_c<1>(am, profile, grid, block, smem, st, p) : score_units_c<2>(am, profile, grid, block, smem, st, p);
   }
   if (C > 2) return cudaErrorInvalidValue;
-  return C == 1 ? score_c<1>(sat, profile, grid, block, smem, st, p) : score_c<2>(sat, profile, grid, block, smem, st, p);
+  return C == 1 ? score_c<1>(am, profile, grid, block, smem, st, p) : score_c<2>(am, profile, grid, block, smem, st, p);
 }
-cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
 #ifdef SWB_HAVE_C4
-  if (C == 4) return trace_c<4>(sat, profile, grid, block, smem, st, p);
+  if (C == 4) return trace_c<4>(am, profile, grid, block, smem, st, p);
 #endif
   if (C > 2) return cudaErrorInvalidValue;
-  return C == 1 ? trace_c<1>(sat, profile, grid, block, smem, st, p) : trace_c<2>(sat, profile, grid, block, smem, st, p);
+  return C == 1 ? trace_c<1>(am, profile, grid, block, smem, st, p) : trace_c<2>(am, profile, grid, block, smem, st, p);
 }
 
 // query-stationary kernels (sw_qs.cuh): one column per step, profile select

@@ -29,9 +29,9 @@ using namespace swb;
 
 // one translation unit per rows-per-lane value R (csrc/sw_inst.cu compiled with -DSWB_R=<R>)
 #define SWB_DECL(RR)                                                                                                  \
-  cudaError_t swb_launch_score_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p); \
-  cudaError_t swb_launch_trace_r##RR(int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p); \
-  cudaError_t swb_launch_dump_r##RR(bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p);       \
+  cudaError_t swb_launch_score_r##RR(int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p); \
+  cudaError_t swb_launch_trace_r##RR(int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p); \
+  cudaError_t swb_launch_dump_r##RR(int am, bool profile, size_t smem, cudaStream_t st, const DumpParams& p);       \
   cudaError_t swb_launch_qs_score_r##RR(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsParams& p); \
   cudaError_t swb_launch_qs_trace_r##RR(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsTraceParams& p);
 SWB_DECL(2) SWB_DECL(4) SWB_DECL(5) SWB_DECL(8) SWB_DECL(12) SWB_DECL(16) SWB_DECL(19) SWB_DECL(24) SWB_DECL(32)
@@ -198,9 +198,10 @@ bool use_profile(const swb_ctx* ctx, bool force_default) {
   return ctx->KP <= 6;
 }
 
-Scoring device_scoring(const HostScoring& hs, bool force_default) {
+Scoring device_scoring(const HostScoring& hs, bool force_default, bool wide = false) {
   int M = force_default ? 3 : hs.M, X = force_default ? 3 : hs.X, G = force_default ? 2 : hs.G;
-  auto pk = [](int v) { return (uint32_t)(uint16_t)(int16_t)v * 0x00010001u; };
+  // two s16 halves per register, or one s32 value (wide lanes, AM_WIDE)
+  auto pk = [wide](int v) { return wide ? (uint32_t)v : (uint32_t)(uint16_t)(int16_t)v * 0x00010001u; };
   Scoring s;
   s.G = G;
   s.negG2 = pk(-G);
@@ -215,8 +216,8 @@ Scoring device_scoring(const HostScoring& hs, bool force_default) {
 // (SAT_U8: one byte per cell, EXACT: 16 bits), for the NB lanes at and above the walker's lane; nlc local checkpoints
 // of the lane state per warp live in HBM scratch.
 struct TraceGeom { int Wc, logWc, NB, nlc; size_t ring_words, scratch_words; };
-TraceGeom trace_geometry(int L, int R, int C, bool sat) {
-  const int PW = sat ? (R + 3) / 4 : (R + 1) / 2;
+TraceGeom trace_geometry(int L, int R, int C, bool sat, bool wide = false) {
+  const int PW = sat ? (R + 3) / 4 : (wide ? R : (R + 1) / 2);
   const int groups = 32 / L;
   // a diagonal walk of Wc columns climbs Wc rows: the walker's lane plus ceil(Wc / R) lanes above it
   auto nb_for = [&](int wc) { return std::min(L, std::max(2, (wc + R - 1) / R + 1)); };
@@ -234,17 +235,17 @@ TraceGeom trace_geometry(int L, int R, int C, bool sat) {
 
 // ---- kernel dispatch: one translation unit per R (sw_inst.cu compiled with -DSWB_R=<R>) ------------------
 
-cudaError_t launch_score(int R, int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
+cudaError_t launch_score(int R, int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
   switch (R) {
-#define SWB_CASE(RR) case RR: return swb_launch_score_r##RR(C, sat, profile, grid, block, smem, st, p);
+#define SWB_CASE(RR) case RR: return swb_launch_score_r##RR(C, am, profile, grid, block, smem, st, p);
     SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
 #undef SWB_CASE
     default: return cudaErrorInvalidValue;
   }
 }
-cudaError_t launch_trace(int R, int C, bool sat, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
+cudaError_t launch_trace(int R, int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
   switch (R) {
-#define SWB_CASE(RR) case RR: return swb_launch_trace_r##RR(C, sat, profile, grid, block, smem, st, p);
+#define SWB_CASE(RR) case RR: return swb_launch_trace_r##RR(C, am, profile, grid, block, smem, st, p);
     SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
 #undef SWB_CASE
     default: return cudaErrorInvalidValue;
@@ -267,9 +268,9 @@ cudaError_t launch_qs_trace(int R, bool sat, dim3 grid, dim3 block, size_t smem,
     default: return cudaErrorInvalidValue;
   }
 }
-cudaError_t launch_dump(int R, bool sat, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
+cudaError_t launch_dump(int R, int am, bool profile, size_t smem, cudaStream_t st, const DumpParams& p) {
   switch (R) {
-#define SWB_CASE(RR) case RR: return swb_launch_dump_r##RR(sat, profile, smem, st, p);
+#define SWB_CASE(RR) case RR: return swb_launch_dump_r##RR(am, profile, smem, st, p);
     SWB_CASE(2) SWB_CASE(4) SWB_CASE(5) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16) SWB_CASE(19) SWB_CASE(24) SWB_CASE(32)
 #undef SWB_CASE
     default: return cudaErrorInvalidValue;
@@ -444,7 +445,7 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
       const uint32_t pair_idx = (uint32_t)lc.pairs.size();
       lc.tasks[order[k]] = TaskDesc{pair_idx, 0u, a.read, a.y_off};
       lc.max_m = std::max(lc.max_m, (int)a.m);
-      if (k + 1 < order.size()) {
+      if (k + 1 < order.size() && !ctx->wide) {          // wide lanes hold one alignment per register: no pair-mate
         const TaskSeed& b = seeds[id[order[k + 1]]];
         if (b.y_off == a.y_off && b.n == a.n) {
           pd.mB = b.m; pd.xB = b.x_off;
@@ -488,6 +489,8 @@ void free_classes(std::vector<LaunchClass>& classes) {
 int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_default, bool select_pieces, bool trace) {
   const HostScoring& hs = ctx->sc;
   const bool sat = hs.mode == SWB_MODE_SAT_U8;
+  const bool wide = ctx->wide && !sat;
+  const int am = sat ? AM_SAT : (wide ? AM_WIDE : AM_EXACT);
   const bool profile = use_profile(ctx, force_default);
   DebugTimer dbg(ctx->stream);
   for (size_t ci = 0; ci < nclasses; ++ci) {
@@ -510,7 +513,8 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     pp.ckpt = ctx->d_ckpt.as<uint32_t>();
     pp.bnd = ctx->d_bnd.as<uint32_t>();
     pp.L = L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
-    pp.sc = device_scoring(hs, force_default);
+    pp.strips = lc.max_strips > 1 ? 1 : 0;
+    pp.sc = device_scoring(hs, force_default, wide);
     if (profile) pp.sc.G = hs.G;
 
     // pack rows
@@ -558,10 +562,10 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
         if (profile) smem = (size_t)ctx->KP * R * 32 * 4;
       }
       const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
-      CUDA_TRY(launch_score(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
+      CUDA_TRY(launch_score(R, ctx->C, am, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
       ctx->stats.kernel_launches++;
       dbg.mark("score", L, R, lc.pairs.size());
-      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nstrips * pd.nblk * ctx->B * ctx->C * L * R * 2ull;
+      for (auto& pd : lc.pairs) ctx->stats.cells_executed += (uint64_t)pd.nstrips * pd.nblk * ctx->B * ctx->C * L * R * (wide ? 1ull : 2ull);
       if (pipelined) {
         uint32_t aborted = 0;
         CUDA_TRY(cudaMemcpyAsync(&aborted, pp.abort_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -580,7 +584,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
       CUDA_TRY(ctx->d_taskmax.ensure(lc.tasks.size() * 4));
       CUDA_TRY(ctx->d_winner.ensure((size_t)lc.nreads * 4));
       const int thr = 128;
-      task_max_kernel<<<(unsigned)((lc.tasks.size() + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.pairs, lc.d_tasks.as<TaskDesc>(), (int)lc.tasks.size(), pp.blkmax, pp.sc.G, ctx->d_taskmax.as<int32_t>());
+      task_max_kernel<<<(unsigned)((lc.tasks.size() + thr - 1) / thr), thr, 0, ctx->stream>>>(pp.pairs, lc.d_tasks.as<TaskDesc>(), (int)lc.tasks.size(), pp.blkmax, pp.sc.G, wide ? 1 : 0, ctx->d_taskmax.as<int32_t>());
       CUDA_TRY(cudaGetLastError());
       select_piece_kernel<<<(unsigned)((lc.nreads + thr - 1) / thr), thr, 0, ctx->stream>>>(ctx->d_taskmax.as<int32_t>(), lc.nreads, lc.pieces, ctx->d_winner.as<uint32_t>());
       CUDA_TRY(cudaGetLastError());
@@ -598,7 +602,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.ntasks = ntrace;
     tp.mode = hs.mode;
     tp.max_pos = force_default ? 3 : std::max(1, hs.max_pos);
-    const TraceGeom tg = trace_geometry(L, R, ctx->C, sat);
+    const TraceGeom tg = trace_geometry(L, R, ctx->C, sat, wide);
     tp.Wc = tg.Wc; tp.logWc = tg.logWc; tp.NB = tg.NB; tp.nlc = tg.nlc;
     const size_t prof_words_warp = profile ? (size_t)ctx->KP * R * 32 : 0;
     warps_per_cta = 4;
@@ -628,7 +632,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     if (dbg.on) { CUDA_TRY(d_cnt.ensure(128)); CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 128, ctx->stream)); tp.counters = d_cnt.as<unsigned long long>(); }
     while (ctx->ev_pool.size() < ctx->ev_used + 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
     CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
-    CUDA_TRY(launch_trace(R, ctx->C, sat, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
+    CUDA_TRY(launch_trace(R, ctx->C, am, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
     CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
     ctx->ev_used += 2;
     ctx->stats.kernel_launches++;
@@ -697,9 +701,9 @@ int stage_qs(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_s
   }
   {
     const uint64_t reach = (uint64_t)std::min<size_t>(max_m, N) * (uint64_t)std::max(1, hs.max_pos) + (uint64_t)hs.G + 16;
-    if (hs.mode == SWB_MODE_EXACT && reach > 32000)
-      return fail(ctx, SWB_ERR_UNSUPPORTED, "EXACT-mode scores may exceed the 16-bit lane range (min(len) * max score = " + std::to_string(reach) + "); the 32-bit path is not built yet");
+    if (hs.mode == SWB_MODE_EXACT && (reach > 32000 || getenv("SWB_FORCE_WIDE"))) return 1;   // wide lanes: the batched kernels
   }
+  ctx->wide = false;
   ctx->C = 1;
   // (s + G) table: rows = reference (query) byte, 256 = padding row; columns = batch code, KP-1 = padding column
   std::vector<int16_t> t((size_t)257 * KP, (int16_t)(-16000));
@@ -1086,11 +1090,14 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
       max_n = std::max(max_n, (size_t)(rg.second - rg.first));
     }
   }
-  // 16-bit lane range: the largest reachable score must stay below 2^15
+  // Lane width: two s16 cells per register while the largest reachable score stays below 2^15, one s32 cell per register
+  // beyond that (AM_WIDE).  The reference's f32 matrix is exact to 2^24 (similaritymatrix.cpp:49-54); past that its own
+  // results are rounded, so there is nothing exact to reproduce and the batch is refused.
   {
     const uint64_t reach = (uint64_t)std::min<size_t>(max_m, max_n) * (uint64_t)std::max(1, hs.max_pos) + (uint64_t)hs.G + 16;
-    if (hs.mode == SWB_MODE_EXACT && reach > 32000)
-      return fail(ctx, SWB_ERR_UNSUPPORTED, "EXACT-mode scores may exceed the 16-bit lane range (min(len) * max score = " + std::to_string(reach) + "); the 32-bit path is not built yet");
+    ctx->wide = hs.mode == SWB_MODE_EXACT && (reach > 32000 || getenv("SWB_FORCE_WIDE"));
+    if (ctx->wide && reach > (1ull << 24))
+      return fail(ctx, SWB_ERR_UNSUPPORTED, "EXACT-mode scores may exceed 2^24 (min(len) * max score = " + std::to_string(reach) + "): the reference's f32 matrix is not exact there either");
   }
   // checkpoint period B (steps between register-state checkpoints): as small as the HBM budget for the
   // checkpoints allows (pass 2 recomputes O(B) columns per alignment), at least 32.
@@ -1269,10 +1276,11 @@ int swb_matrix(swb_ctx* ctx, const char* x, size_t m, int32_t* out) {
   pp.pairs = lc.d_pairs.as<PairDesc>(); pp.npairs = 1;
   pp.blkmax = ctx->d_blkmax.as<uint32_t>(); pp.ckpt = ctx->d_ckpt.as<uint32_t>(); pp.bnd = ctx->d_bnd.as<uint32_t>();
   pp.L = lc.geo.L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
-  pp.sc = device_scoring(ctx->sc, false);
+  const bool wide = ctx->wide && !sat;
+  pp.sc = device_scoring(ctx->sc, false, wide);
   dp.out = d_out.as<int32_t>(); dp.m = (int)m; dp.n = (int)n;
   const size_t smem = profile ? (size_t)ctx->KP * lc.geo.R * 32 * 4 : 0;
-  cudaError_t e = launch_dump(lc.geo.R, sat, profile, smem, ctx->stream, dp);
+  cudaError_t e = launch_dump(lc.geo.R, sat ? AM_SAT : (wide ? AM_WIDE : AM_EXACT), profile, smem, ctx->stream, dp);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, (m + 1) * (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   d_out.release();

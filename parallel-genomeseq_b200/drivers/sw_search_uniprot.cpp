@@ -8,7 +8,10 @@
 // offsets), all proteins go through ONE batched call, and the same CSV is written by the same process.
 // Several GPUs (--gpus G, 0 = all): the database is partitioned by residues over G GPUs, one host thread each, and the
 // rows are written in database order (mpi_sw_solve_uniprot.cpp:65-72 gives every rank a block of files).
-//   sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M] [--gpus G]
+//   sw_search_uniprot QUERY.fasta DB.fasta|DB.swbdb OUT.csv [--blosum62 GAP] [--first N --count M] [--gpus G]
+//   sw_search_uniprot --pack DB.fasta DB.swbdb        convert a multi-FASTA database into the packed 5-bit blob once
+//     A database whose name ends in .swbdb is the packed blob (cpp/packed_db.h): no FASTA parsing per run; rows are written
+//     in the ORIGINAL database order.
 //     default scoring = the reference's (a == b ? 3 : -3, gap 2); --blosum62 10 tabulates BLOSUM62 through the
 //     callback constructor surface (smithwaterman.h:16-17) with linear gap 10.
 #include <cstdio>
@@ -19,7 +22,10 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+
 #include "../cpp/cuda_aligner.h"
+#include "../cpp/packed_db.h"
 
 static const char* kOrder = "ARNDCQEGHILKMFPSTWYVBZX*";
 static const int kBlosum62[24][24] = {
@@ -53,23 +59,48 @@ static bool read_fasta_records(const std::string& path, std::vector<std::string>
 
 int main(int argc, char** argv) {
   std::vector<std::string> pos;
-  bool blosum = false; float gap = 2.f; size_t first = 0, count = (size_t)-1; int gpus = 1;
+  bool blosum = false, pack = false; float gap = 2.f; size_t first = 0, count = (size_t)-1; int gpus = 1;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--blosum62") && i + 1 < argc) { blosum = true; gap = (float)std::atof(argv[++i]); }
     else if (!std::strcmp(argv[i], "--first") && i + 1 < argc) first = (size_t)std::atoll(argv[++i]);
     else if (!std::strcmp(argv[i], "--count") && i + 1 < argc) count = (size_t)std::atoll(argv[++i]);
     else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--pack")) pack = true;
     else pos.push_back(argv[i]);
   }
-  if (pos.size() < 3) { std::cerr << "usage: sw_search_uniprot QUERY.fasta DB.fasta OUT.csv [--blosum62 GAP] [--first N --count M]" << std::endl; return 2; }
+  if (pack) {
+    if (pos.size() < 2) { std::cerr << "usage: sw_search_uniprot --pack DB.fasta DB.swbdb" << std::endl; return 2; }
+    std::vector<std::string> db;
+    if (!read_fasta_records(pos[0], &db) || db.empty()) { std::cerr << "cannot read database " << pos[0] << std::endl; return 2; }
+    if (!swb::write_packed_db(db, pos[1])) { std::cerr << "cannot write " << pos[1] << std::endl; return 2; }
+    std::cout << "Packed " << db.size() << " entries into " << pos[1] << std::endl;
+    return 0;
+  }
+  if (pos.size() < 3) { std::cerr << "usage: sw_search_uniprot QUERY.fasta DB.fasta|DB.swbdb OUT.csv [--blosum62 GAP] [--first N --count M] [--gpus G]" << std::endl; return 2; }
   std::vector<std::string> q, db;
   if (!read_fasta_records(pos[0], &q) || q.empty()) { std::cerr << "cannot read query " << pos[0] << std::endl; return 2; }
-  if (!read_fasta_records(pos[1], &db) || db.empty()) { std::cerr << "cannot read database " << pos[1] << std::endl; return 2; }
+  const auto t_stage0 = std::chrono::steady_clock::now();
+  const bool packed = pos[1].size() > 6 && pos[1].compare(pos[1].size() - 6, 6, ".swbdb") == 0;
+  swb::PackedDb pdb;
+  std::vector<std::string_view> all;           // every database entry, in the order it is stored
+  std::vector<size_t> orig;                    // its index in the original database
+  if (packed) {
+    std::string err;
+    if (!swb::load_packed_db(pos[1], &pdb, &err)) { std::cerr << err << std::endl; return 2; }
+    for (size_t i = 0; i < pdb.size(); ++i) { all.emplace_back(pdb.blob.data() + pdb.offsets[i], pdb.offsets[i + 1] - pdb.offsets[i]); orig.push_back(pdb.orig[i]); }
+  } else {
+    if (!read_fasta_records(pos[1], &db) || db.empty()) { std::cerr << "cannot read database " << pos[1] << std::endl; return 2; }
+    for (size_t i = 0; i < db.size(); ++i) { all.emplace_back(db[i]); orig.push_back(i); }
+  }
+  const double stage_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_stage0).count();
   const std::string& fa_string = q[0];
-  if (first > db.size()) first = db.size();
-  if (count > db.size() - first) count = db.size() - first;
+  // --first / --count select by ORIGINAL index
+  const size_t ndb = all.size();
+  if (first > ndb) first = ndb;
+  if (count > ndb - first) count = ndb - first;
   std::vector<std::string_view> xs;
-  for (size_t i = first; i < first + count; ++i) xs.emplace_back(db[i]);
+  std::vector<size_t> row_of;                  // output row (original order) of every aligned entry
+  for (size_t i = 0; i < ndb; ++i) if (orig[i] >= first && orig[i] < first + count) { xs.push_back(all[i]); row_of.push_back(orig[i] - first); }
 
   auto blosum_fn = [](const char& a, const char& b) -> float {
     const char* pa = std::strchr(kOrder, a); const char* pb = std::strchr(kOrder, b);
@@ -96,12 +127,16 @@ int main(int argc, char** argv) {
   csv << "read,pos_pred,score\n";
   unsigned long long cells = 0;
   char buff[127];
-  for (size_t i = 0; i < xs.size(); ++i) {
-    std::snprintf(buff, sizeof buff, "%.126s", db[first + i].c_str());
+  std::vector<size_t> at(xs.size());           // aligned entry of every output row
+  for (size_t i = 0; i < xs.size(); ++i) at[row_of[i]] = i;
+  for (size_t r = 0; r < xs.size(); ++r) {
+    const size_t i = at[r];
+    std::snprintf(buff, sizeof buff, "%.126s", std::string(xs[i]).c_str());
     csv << buff << ", " << (int)out.pos[i] << ", " << (double)out.score[i] << "\n";
     cells += (unsigned long long)xs[i].size() * fa_string.size();
   }
   std::cout << "Searched " << xs.size() << " proteins against a " << fa_string.size() << "-residue query: device time "
-            << out.device_us * 1e-3 << " ms, GCUPS " << cells / (double)out.device_us * 1e-3 << std::endl;
+            << out.device_us * 1e-3 << " ms, GCUPS " << cells / (double)out.device_us * 1e-3 << " (database " << (packed ? "packed blob" : "FASTA")
+            << " read in " << stage_s << " s)" << std::endl;
   return 0;
 }

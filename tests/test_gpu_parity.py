@@ -310,12 +310,50 @@ def test_edge_cases_against_oracle(engine, pkg):
             _check(r, i, o.align(x, ref, mode=o.MODE_SAT_U8), tag=("short-ref", ref, i))
 
 
-def test_exact_mode_overflow_is_refused(engine, pkg):
-    """EXACT scores that could leave the 16-bit lanes are refused loudly, never computed wrongly."""
-    engine.set_scoring_match(pkg.MODE_EXACT, 100, -3, 2)
-    engine.set_reference("ACGT" * 200)
+def test_exact_scores_beyond_16_bits_use_wide_lanes(engine, pkg, monkeypatch):
+    """Similarity_Matrix is exact to 2^24 (f32, similaritymatrix.cpp:49-54).  EXACT scores that could leave the 16-bit
+    lanes run with one s32 cell per register (AM_WIDE) — batched kernels, row strips, pipelined strips, chunking, the
+    dense-matrix accessor — against the oracle; beyond 2^24 the batch is refused loudly, never computed wrongly."""
+    rng = np.random.default_rng(123)
+    y = "".join(rng.choice(list("ACGT"), size=2100))
+    xs = []
+    for m, s0 in ((600, 100), (601, 900), (40, 5), (1500, 300), (333, 1700), (1100, 0)):
+        x = list((y * 2)[s0:s0 + m])
+        for q in range(m):
+            if rng.random() < 0.05:
+                x[q] = str(rng.choice(list("ACGT")))
+        xs.append("".join(x))
+    for (ma, mi, g) in ((100, -90, 40), (1000, -3, 2)):
+        engine.set_scoring_match(pkg.MODE_EXACT, ma, mi, g)
+        engine.set_reference(y)
+        r = engine.align(xs, cons_stride=5000)
+        assert max(int(v) for v in r["score"]) > 40_000
+        for i, x in enumerate(xs):
+            w = o.align(x, y, mode=o.MODE_EXACT, match=ma, mismatch=mi, gap=g)
+            _check(r, i, w, tag=("wide", ma, len(x)))
+            assert tuple(r["end"][i]) == w["end"]
+        rc = engine.align(xs[:3], npiece=3, ratio=1.5, cons_stride=5000)
+        for i, x in enumerate(xs[:3]):
+            _check(rc, i, o.align_chunked(x, y, 3, 1.5, mode=o.MODE_EXACT, match=ma, mismatch=mi, gap=g), tag=("wide-chunked", ma, i))
+    engine.set_scoring_match(pkg.MODE_EXACT, 100, -90, 40)
+    engine.set_reference(y[:300])
+    assert (engine.matrix(xs[2]) == o.matrix(xs[2], y[:300], mode=o.MODE_EXACT, match=100, mismatch=-90, gap=40)).all()
+    # the wide kernels on ordinary scores (forced): identical results to the 16-bit lanes, incl. pipelined strips
+    monkeypatch.setenv("SWB_FORCE_WIDE", "1")
+    ref = synth.c3_reference(60_000, seed=41)
+    reads = synth.mutated_reads(ref, 3, 2_500, seed=42, sub=0.03, ins=0.003, dele=0.003)
+    engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
+    engine.set_reference(ref)
+    r = engine.align(reads, cons_stride=8_000)
+    assert engine.stats()["kernel_kind"] == 1
+    for i, x in enumerate(reads):
+        w = o.align(x, ref, mode=o.MODE_EXACT, linear=True)
+        _check(r, i, w, tag=("wide-units", len(x)))
+    monkeypatch.delenv("SWB_FORCE_WIDE")
+    engine.set_scoring_match(pkg.MODE_EXACT, 4000, -3, 2)
+    engine.set_reference("ACGT" * 2000)
     with pytest.raises(pkg.SwbError) as ei:
-        engine.align(["ACGT" * 150])
+        engine.align(["ACGT" * 1500])
     assert ei.value.code == -5
     engine.set_scoring_match(pkg.MODE_EXACT, 3, -3, 2)
 
@@ -637,6 +675,14 @@ def test_drivers_over_several_gpus(tmp_path, data_small, c4_sample):
     for line, e in zip(rows[1:], c4_sample["entries"]):
         f_ = line.split(", ")
         assert int(f_[1]) == e["pos"] and float(f_[2]) == e["score"]
+    # the packed 5-bit database blob: same rows in the original database order, no FASTA parsing per run
+    packed = tmp_path / "db.swbdb"
+    r = subprocess.run([os.path.join(ddir, "sw_search_uniprot"), "--pack", str(db), str(packed)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out2 = tmp_path / "out2.csv"
+    r = subprocess.run([os.path.join(ddir, "sw_search_uniprot"), str(q), str(packed), str(out2), "--blosum62", str(c4_sample["gap"])], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "packed blob" in r.stdout, r.stdout + r.stderr
+    assert out2.read_text() == out_csv.read_text()
 
 
 def test_rebind_reference_keeps_the_database_resident(engine, pkg):

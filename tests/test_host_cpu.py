@@ -218,3 +218,64 @@ def test_reference_headers_mode_compiles():
         pytest.skip("needs /root/reference (build container)")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpp", "build_ref_tests.py"), "--force"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and os.path.isfile(os.path.join(ROOT, "tests", "cpp", "ref_test_localaligner")), r.stdout + r.stderr
+
+
+def test_dataprep_tools(tmp_path):
+    """the dependency-free data preparation — SAM -> ground-truth CSV, FASTQ -> one read per line, custom
+    reference / read generation, multi-FASTA splitting and the packed 5-bit database blob.  In the build container the
+    SAM the reference ships must reproduce the reference's own data_small_ground_truth.csv byte for byte."""
+    import importlib
+    dp = importlib.import_module("parallel-genomeseq_b200.dataprep")
+    sam = tmp_path / "t.sam"
+    sam.write_text("@HD\tVN:1.0\n@SQ\tSN:22_5K\tLN:4980\nr1\t99\t22_5K\t17\t60\t5M\t=\t40\t28\tACGTA\tIIIII\tNM:i:0\nr2\t147\t22_5K\t40\t60\t4M\t=\t17\t-28\tGGCC\tIIII\n")
+    assert dp.sam_to_ground_truth(str(sam), str(tmp_path / "gt.csv")) == 2
+    assert (tmp_path / "gt.csv").read_text() == "index,QNAME,SEQ,POS\n0,r1,ACGTA,17\n1,r2,GGCC,40\n"
+    ref_sam = "/root/reference/data/data_small/output_tiny_30xCov.mod.sam"
+    if os.path.isfile(ref_sam):
+        dp.sam_to_ground_truth(ref_sam, str(tmp_path / "gt_ref.csv"))
+        with open("/root/reference/data/data_small_ground_truth.csv") as f:
+            assert (tmp_path / "gt_ref.csv").read_text() == f.read()
+        with open(os.path.join(ROOT, "tests", "golden", "data_small", "data_small_ground_truth.csv")) as f:
+            assert (tmp_path / "gt_ref.csv").read_text() == f.read()
+    fq = tmp_path / "t.fq"
+    fq.write_text("@a\nACGT\n+\nIIII\n@b\nTTGA\n+\nIIII\n")
+    assert dp.fastq_sequences(str(fq), str(tmp_path / "lines.txt")) == ["ACGT", "TTGA"] and (tmp_path / "lines.txt").read_text() == "ACGT\nTTGA\n"
+    fa = tmp_path / "long.fa"
+    fa.write_text(">chr\n" + "acgtn" * 4 + "\n" + "GGCCN" * 4 + "\n" + "TTTTT" * 4 + "\n")
+    assert dp.read_fa(str(fa)) == "acgtn" * 4 + "GGCCN" * 4 + "TTTTT" * 4
+    assert dp.gen_ref_custom(str(fa), str(tmp_path / "ref.fa"), start_pos=20, ref_len=20) == "GGCC" * 4      # the line that starts in the window, N removed
+    rows = dp.gen_reads_custom(str(tmp_path / "ref.fa"), str(tmp_path / "reads.csv"), read_len=5, n_reads=7, seed=3)
+    lines = (tmp_path / "reads.csv").read_text().strip().split("\n")
+    assert lines[0] == "index,QNAME,SEQ,POS" and len(lines) == 8 and all(("GGCC" * 4)[p:p + 5] == s for _, s, p in rows)
+    assert (tmp_path / "reads_readsonly.txt").read_text().count("\n") == 7
+    mf = tmp_path / "db.fasta"
+    prots = ["MKV", "ARNDCQEGHILKMFPSTWYVBZX", "MKTAYIAKQRQISFVKSHFSRQ", "uoj", "A"]
+    mf.write_text("".join(f">sp|P{i}|x\n{p[:10]}\n{p[10:]}\n" for i, p in enumerate(prots)))
+    assert dp.split_multifasta(str(mf), str(tmp_path / "database.fasta"), str(tmp_path / "stats.txt")) == 5
+    assert (tmp_path / "stats.txt").read_text() == "5" and (tmp_path / "database.fasta").read_text().split("\n")[1] == prots[1]
+    assert dp.pack_database(str(mf), str(tmp_path / "db.swbdb")) == (5, sum(len(p) for p in prots))
+    blob, offs, orig = dp.load_database(str(tmp_path / "db.swbdb"))
+    got = [blob[int(offs[i]):int(offs[i + 1])].tobytes().decode() for i in range(5)]
+    assert [len(g) for g in got] == sorted((len(p) for p in prots), reverse=True)
+    assert {int(o_): g for o_, g in zip(orig, got)} == {i: p.upper() for i, p in enumerate(prots)}
+    assert os.path.getsize(tmp_path / "db.swbdb") < 8 + 20 + 32 + 4 * 5 + 8 * 6 + sum(len(p) for p in prots)      # 5 bits per residue
+
+
+def test_packed_database_cpp_and_python_agree(tmp_path):
+    """The packed 5-bit database written by the C++ driver (sw_search_uniprot --pack, cpp/packed_db.h) is byte-identical to
+    the one parallel-genomeseq_b200/dataprep.py writes (no GPU involved)."""
+    import importlib
+    dp = importlib.import_module("parallel-genomeseq_b200.dataprep")
+    drv = os.path.join(ROOT, "parallel-genomeseq_b200", "drivers", "sw_search_uniprot")
+    if not os.path.isfile(drv):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(drv)])
+    synth = importlib.import_module("parallel-genomeseq_b200.synth")
+    prots = synth.c4_database(300, seed=3) + ["MKV", "x*u", "A"]
+    mf = tmp_path / "db.fasta"
+    mf.write_text("".join(f">sp|P{i}|x\n" + "\n".join(p[k:k + 60] for k in range(0, len(p), 60)) + "\n" for i, p in enumerate(prots)))
+    r = subprocess.run([drv, "--pack", str(mf), str(tmp_path / "cpp.swbdb")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    dp.pack_database(str(mf), str(tmp_path / "py.swbdb"))
+    assert (tmp_path / "cpp.swbdb").read_bytes() == (tmp_path / "py.swbdb").read_bytes()
+    blob, offs, orig = dp.load_database(str(tmp_path / "cpp.swbdb"))
+    assert blob[int(offs[0]):int(offs[1])].tobytes().decode() == max(prots, key=len).upper()

@@ -61,7 +61,7 @@ def main():
         if rng.random() < 0.5:
             os.environ.pop("SWB_SELECT", None); os.environ.pop("SWB_COLS", None)
         # pass-2 knobs: ring depth, band lanes (2 = a new session every few rows), checkpoint period
-        for k, choices in (("SWB_TRACE_WC", ["32", "64"]), ("SWB_TRACE_NB", ["2", "3", "5"]), ("SWB_FORCE_B", ["32", "64", "256", "1024"])):
+        for k, choices in (("SWB_TRACE_WC", ["32", "64"]), ("SWB_TRACE_NB", ["2", "3", "5"]), ("SWB_FORCE_B", ["32", "64", "256", "1024"]), ("SWB_FORCE_WIDE", ["1"])):
             if rng.random() < 0.4:
                 os.environ[k] = str(rng.choice(choices))
             else:
@@ -92,7 +92,7 @@ def main():
             checked += 1
             if not ok:
                 print("MISMATCH iter", it, "read", i, "mode", mode, "m", len(x), "n", n, "npiece", npiece, ratio, "scoring", (ma, mi, gap2) if table is None else ("table", gap),
-                      "env", {k: os.environ.get(k) for k in ("SWB_SELECT", "SWB_COLS", "SWB_CHUNK_PAIRS", "SWB_QSTAT", "SWB_TRACE_WC", "SWB_TRACE_NB", "SWB_FORCE_B")})
+                      "env", {k: os.environ.get(k) for k in ("SWB_SELECT", "SWB_COLS", "SWB_CHUNK_PAIRS", "SWB_QSTAT", "SWB_TRACE_WC", "SWB_TRACE_NB", "SWB_FORCE_B", "SWB_FORCE_WIDE")})
                 print(" flags", int(r["flags"][i]))
                 print(" got ", int(r["score"][i]), int(r["pos"][i]), tuple(r["end"][i]), len(r["cx"][i]))
                 print(" want", w["score"], w["pos"], w.get("end"), len(w["cx"]))

@@ -30,14 +30,14 @@ FMA = {"IMAD", "HFMA2", "FFMA", "FMUL", "FADD", "IDP"}
 # key -> (object, mangled kernel, DP instructions that identify the loop, cell pairs per lane per loop trip)
 #   loop trip = two wavefront steps of R rows x C columns
 KERNELS = {
-    "c3  score_kernel<R=19,C=1,SAT,profile>  (8 lanes x 19 rows)": ("sw_inst_r19.o", "_ZN3swb12score_kernelILi19ELi1ELb1ELb1EEEvNS_10PassParamsE", 2 * 19 * 1),
-    "c1x64/c2x64  score_kernel<R=16,C=1,SAT,profile>  (8 lanes x 16 rows)": ("sw_inst_r16.o", "_ZN3swb12score_kernelILi16ELi1ELb1ELb1EEEvNS_10PassParamsE", 2 * 16 * 1),
-    "c1/c2 x1  score_kernel<R=4,C=2,SAT,profile>  (32 lanes x 4 rows, 2 columns)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi2ELb1ELb1EEEvNS_10PassParamsE", 2 * 4 * 2),
-    "c2 x1  score_kernel<R=4,C=1,SAT,profile>  (32 lanes x 4 rows)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi1ELb1ELb1EEEvNS_10PassParamsE", 2 * 4 * 1),
+    "c3  score_kernel<R=19,C=1,SAT,profile>  (8 lanes x 19 rows)": ("sw_inst_r19.o", "_ZN3swb12score_kernelILi19ELi1ELi1ELb1EEEvNS_10PassParamsE", 2 * 19 * 1),
+    "c1x64/c2x64  score_kernel<R=16,C=1,SAT,profile>  (8 lanes x 16 rows)": ("sw_inst_r16.o", "_ZN3swb12score_kernelILi16ELi1ELi1ELb1EEEvNS_10PassParamsE", 2 * 16 * 1),
+    "c1/c2 x1  score_kernel<R=4,C=2,SAT,profile>  (32 lanes x 4 rows, 2 columns)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi2ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 2),
+    "c2 x1  score_kernel<R=4,C=1,SAT,profile>  (32 lanes x 4 rows)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi1ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 1),
     "c4  qs_score_kernel<R=19,EXACT>  (16 lanes x 19 rows, query-stationary)": ("sw_inst_r19.o", "_ZN3swb15qs_score_kernelILi19ELb0EEEvNS_8QsParamsE", 2 * 19 * 1),
-    "c5  score_units_kernel<R=8,C=4,EXACT,profile>  (pipelined strips)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi4ELb0ELb1EEEvNS_10PassParamsE", 2 * 8 * 4),
-    "c5  score_units_kernel<R=8,C=4,SAT,profile>  (pipelined strips)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi4ELb1ELb1EEEvNS_10PassParamsE", 2 * 8 * 4),
-    "c5  score_units_kernel<R=4,C=4,EXACT,profile>  (pipelined strips, short references)": ("sw_inst_r4.o", "_ZN3swb18score_units_kernelILi4ELi4ELb0ELb1EEEvNS_10PassParamsE", 2 * 4 * 4),
+    "c5  score_units_kernel<R=8,C=4,EXACT,profile>  (pipelined strips)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi4ELi0ELb1EEEvNS_10PassParamsE", 2 * 8 * 4),
+    "c5  score_units_kernel<R=8,C=4,SAT,profile>  (pipelined strips)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi4ELi1ELb1EEEvNS_10PassParamsE", 2 * 8 * 4),
+    "c5  score_units_kernel<R=4,C=4,EXACT,profile>  (pipelined strips, short references)": ("sw_inst_r4.o", "_ZN3swb18score_units_kernelILi4ELi4ELi0ELb1EEEvNS_10PassParamsE", 2 * 4 * 4),
 }
 
 
