@@ -545,12 +545,12 @@ __device__ __forceinline__ void score_pass(Wavefront<R, C, AM, PROFILE>& wf, con
   }
 }
 
-// Resident thread blocks per SM the score kernels are compiled for: 4 x 128 threads (16 warps) up to 19 rows per lane —
-// the register bound (<= 128) that keeps the hot loop at its measured occupancy whatever ptxas would otherwise pick
-// (round 2: an unrelated edit let it take 138 registers, 3 blocks per SM, 84 % instead of 88 % ALU-pipe busy).
-#ifndef SWB_SCORE_MINBLOCKS
-#define SWB_SCORE_MINBLOCKS(R) ((R) <= 19 ? 4 : ((R) <= 24 ? 3 : 2))
-#endif
+// score_kernel must keep 4 thread blocks of 128 threads resident per SM (16 warps): at most 128 registers per thread up to
+// 19 rows per lane.  ptxas is left free to pick its allocation (forcing the bound with __launch_bounds__(128, 4) or
+// __maxnreg__(128) costs 5-18 instructions in the hot loop and 2 % of its scheduled cycles: 206 / 219 vs 201 instructions
+// per 38 cell pairs, measured 8.44 vs 8.63 TCUPS on one box); instead the register count of
+// the built kernels is CHECKED by tools/sass_counts.py --check (a CPU test): round 2 once let an unrelated edit take it
+// to 138 registers, 3 blocks per SM and 84 % instead of 88 % ALU-pipe busy without anything failing.
 // The batched kernel exists twice: score_kernel for classes whose pairs all fit ONE strip (every read-mapping batch: the
 // hot kernel of the C3 benchmark) and score_strips_kernel for classes with row strips run top to bottom by one warp.
 // ptxas allocates registers and schedules per kernel, so keeping the strip loop out of score_kernel keeps its hot loop
@@ -593,7 +593,7 @@ __device__ __forceinline__ void score_batched(const PassParams& p, uint32_t* sme
 }
 
 template <int R, int C, int AM, bool PROFILE>
-__global__ void __launch_bounds__(128, SWB_SCORE_MINBLOCKS(R)) score_kernel(const PassParams p) {
+__global__ void __launch_bounds__(128, 1) score_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
   score_batched<R, C, AM, PROFILE, false>(p, smem_prof);
 }
@@ -697,7 +697,8 @@ __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
   const int n = (int)pd.n;
   const int nb = (int)pd.nblk;
   // publishing costs a fence, waiting for it costs pipeline lag down the chain of strips: balance the two
-  const int pub_every = max(1, min(16, (int)sqrtf(0.1f * (float)nb / (float)max(1u, pd.nstrips))));
+  // (a fence per block is nothing once a block is a few hundred steps; finer progress lets the strips below absorb jitter)
+  const int pub_every = p.B >= 256 ? 1 : max(1, min(16, (int)sqrtf(0.1f * (float)nb / (float)max(1u, pd.nstrips))));
   int since_pub = 0;
   wf.template begin<true>(pd, 0);
   wf.chunk_next2 = wf.load_chunk(pd, 1);
@@ -1047,7 +1048,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
         const int row_lo = ss * S;                           // last row of the strip above (0 for strip 0)
         const uint32_t* above = ss > 0 ? p.bnd + pd.bnd_off + (size_t)(ss - 1) * (n + 1) : nullptr;
         const int i_min = row_lo + band_lo * R + 1;          // first row the ring holds
-        const int j_min = C * (t_store - band_lo - 1) + 1;   // first column EVERY band lane holds (lane g holds t_store - g onwards)
+        // first column the ring holds for row i: its lane gg kept the steps from t_store on, i.e. columns from
+        // C * (t_store - gg - 1) + 1 (lower lanes started later, so the row ABOVE the walker is the binding one)
+        auto j_min_of = [&](int i) -> int { return C * (t_store - band_lo - (i - i_min) / R - 1) + 1; };
         // H(i, j) from the ring (both inside it): one byte (SAT_U8: E mod 256) or one signed 16-bit (EXACT: E) load
         auto ring_val = [&](int i, int j) -> int {
           const int r = i - i_min;
@@ -1062,14 +1065,14 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
         auto cell = [&](int i, int j) -> int {
           if (i <= 0 || j <= 0) return 0;
           if (i == row_lo) return lane_val<WIDE>(__ldcg(above + j), half) + G;
-          if (i < i_min || j < j_min) return -1;
+          if (i < i_min || j < j_min_of(i)) return -1;
           return ring_val(i, j);
         };
         const int ix0 = ix, iy0 = iy;
         while (!(tp.dbg_flags & 2)) {
           if (ix <= row_lo) break;                           // walked into the strip above: next session there
           int vd, vu, vl;                                    // H(ix-1, iy-1), H(ix-1, iy), H(ix, iy-1)
-          if (ix - 1 >= i_min && iy - 1 >= j_min) { vd = ring_val(ix - 1, iy - 1); vu = ring_val(ix - 1, iy); vl = ring_val(ix, iy - 1); }
+          if (ix - 1 >= i_min && iy - 1 >= j_min_of(ix - 1)) { vd = ring_val(ix - 1, iy - 1); vu = ring_val(ix - 1, iy); vl = ring_val(ix, iy - 1); }
           else {
             vd = cell(ix - 1, iy - 1); vu = cell(ix - 1, iy); vl = cell(ix, iy - 1);
             if ((vd | vu | vl) < 0) break;                   // left the ring: next session starts at (ix, iy)

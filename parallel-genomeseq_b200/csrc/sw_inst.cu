@@ -59,12 +59,13 @@ cudaError_t SWB_CAT(swb_launch_dump_r, SWB_R)(int am, bool profile, size_t smem,
 // Four columns per step exist for the pipelined strips of few long pairs only (score_units_kernel and the pass-2 kernel
 // that replays its checkpoints), and only for thin strips.
 #if SWB_R <= 8
-#define SWB_HAVE_C4 1
+#define SWB_HAVE_C4 1      // and eight columns per step
 #endif
 cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PassParams& p) {
   if (p.units) {
 #ifdef SWB_HAVE_C4
     if (C == 4) return score_units_c<4>(am, profile, grid, block, smem, st, p);
+    if (C == 8) return score_units_c<8>(am, profile, grid, block, smem, st, p);
 #endif
     if (C > 2) return cudaErrorInvalidValue;
     return C == 1 ? score_units_c<1>(am, profile, grid, block, smem, st, p) : score_units_c<2>(am, profile, grid, block, smem, st, p);
@@ -75,6 +76,7 @@ cudaError_t SWB_CAT(swb_launch_score_r, SWB_R)(int C, int am, bool profile, dim3
 cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, int am, bool profile, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TraceParams& p) {
 #ifdef SWB_HAVE_C4
   if (C == 4) return trace_c<4>(am, profile, grid, block, smem, st, p);
+  if (C == 8) return trace_c<8>(am, profile, grid, block, smem, st, p);
 #endif
   if (C > 2) return cudaErrorInvalidValue;
   return C == 1 ? trace_c<1>(am, profile, grid, block, smem, st, p) : trace_c<2>(am, profile, grid, block, smem, st, p);

@@ -220,12 +220,16 @@ TraceGeom trace_geometry(int L, int R, int C, bool sat, bool wide = false) {
   const int PW = sat ? (R + 3) / 4 : (wide ? R : (R + 1) / 2);
   const int groups = 32 / L;
   // a diagonal walk of Wc columns climbs Wc rows: the walker's lane plus ceil(Wc / R) lanes above it
-  auto nb_for = [&](int wc) { return std::min(L, std::max(2, (wc + R - 1) / R + 1)); };
+  // A lane k lanes above the walker's holds C * (Wc - k) columns left of the walker, and a diagonal walk reaches it after
+  // k * R columns: a session ends after about C * Wc * R / (R + C) columns, in lane ceil(C * Wc / (R + C)) above.
+  auto nb_for = [&](int wc) { return std::min(L, std::max(2, (wc * C + R + C - 1) / (R + C) + 1)); };
   auto bytes_for = [&](int wc) { return (size_t)wc * C * PW * groups * nb_for(wc) * 4; };
   int wc = bytes_for(64) <= 16 * 1024 ? 64 : 32;
   if (const char* e = getenv("SWB_TRACE_WC")) wc = std::max(32, std::min(256, 1 << ilog2(atoi(e))));   // >= 32: strip replays restart on 32-column chunks
   TraceGeom t;
   t.Wc = wc; t.logWc = ilog2(wc); t.NB = nb_for(wc);
+  // wide strips with many columns per step: keep one warp's ring under 96 KB (fewer band lanes only shorten a session)
+  while (t.NB > 2 && (size_t)wc * C * PW * groups * t.NB * 4 > 96 * 1024) --t.NB;
   if (const char* e = getenv("SWB_TRACE_NB")) t.NB = std::min(L, std::max(L > 1 ? 2 : 1, atoi(e)));
   t.nlc = 8;
   t.ring_words = (size_t)wc * C * PW * groups * t.NB;
@@ -316,10 +320,11 @@ int strip_rows(const swb_ctx* ctx, uint32_t m_max, uint32_t n_max, size_t npairs
   if (few_long) *few_long = false;
   if (npairs_est < 148 * 8 && (int)m_max > 32 * r_strip) {
     if (few_long) *few_long = true;
-    // boundary rows: up to half of the free HBM (at least 32 GiB), SWB_BND_BUDGET_MB overrides
+    // boundary rows: up to three quarters of the free HBM (at least 32 GiB), SWB_BND_BUDGET_MB overrides.  10 kbp x 51 Mbp:
+    // 4 rows per lane need 127 GB (79 strips per pair, 632 warps), 8 rows 64 GB (320 warps)
     size_t budget_mb = 32768;
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget_mb = std::max<size_t>(budget_mb, (free_b + ctx->d_bnd.cap) / 2 / 1048576);
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget_mb = std::max<size_t>(budget_mb, (free_b + ctx->d_bnd.cap) / 4 * 3 / 1048576);
     if (const char* e = getenv("SWB_BND_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
     for (int i = kNumR - 1; i >= 0; --i) {
       const int R = kRSet[i];
@@ -1116,9 +1121,9 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     bool few_long = false;
     const int r_long = strip_rows(ctx, max_m, (uint32_t)max_n, (seeds.size() + 1) / 2, use_profile(ctx, false), &few_long);
     const bool c4_ok = !ctx->force_l32 && few_long && r_long <= 8 && min_m > (uint32_t)(32 * r_long) && !getenv("SWB_NO_PIPELINE");
-    if (c4_ok) ctx->C = 4;
+    if (c4_ok) ctx->C = 8;      // measured at 10 kbp x 51 Mbp: 2.20 / 2.40 TCUPS at 4 / 8 columns per step (8 rows per lane), 2.43 / 2.55 (4 rows)
     if (ctx->force_l32) ctx->C = 1;
-    else if (const char* e = getenv("SWB_COLS")) { const int c = atoi(e); ctx->C = (c == 4 && c4_ok) ? 4 : (c >= 2 ? 2 : 1); }
+    else if (const char* e = getenv("SWB_COLS")) { const int c = atoi(e); ctx->C = ((c == 4 || c == 8) && c4_ok) ? c : (c >= 2 ? 2 : 1); }
     while (B < 65536 && words_per_block * 4.0 * ((double)max_n / ((double)B * ctx->C) + 1.0) > (double)budget_mb * 1048576.0) B <<= 1;
     // SWB_FORCE_B: run small test batches with the checkpoint period a large batch would get (parity of the timed geometry)
     if (const char* e = getenv("SWB_FORCE_B")) B = std::max(32, std::min(65536, 1 << ilog2(atoi(e))));

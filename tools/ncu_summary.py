@@ -14,10 +14,17 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
-def main(path):
+def main(path, which=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[-1]
+    hdr, units = rows[0], rows[1]
+    sel = [r for r in rows[2:] if which is None or which in r[hdr.index("Kernel Name")]]
+    for vals in (sel if which else sel[-1:]):
+        one(hdr, units, vals)
+        print()
+
+
+def one(hdr, units, vals):
     for k in KEYS:
         if k in hdr:
             i = hdr.index(k)
@@ -36,4 +43,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)

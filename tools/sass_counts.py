@@ -35,22 +35,32 @@ KERNELS = {
     "c1/c2 x1  score_kernel<R=4,C=2,SAT,profile>  (32 lanes x 4 rows, 2 columns)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi2ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 2),
     "c2 x1  score_kernel<R=4,C=1,SAT,profile>  (32 lanes x 4 rows)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi1ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 1),
     "c4  qs_score_kernel<R=19,EXACT>  (16 lanes x 19 rows, query-stationary)": ("sw_inst_r19.o", "_ZN3swb15qs_score_kernelILi19ELb0EEEvNS_8QsParamsE", 2 * 19 * 1),
-    "c5  score_units_kernel<R=8,C=4,EXACT,profile>  (pipelined strips)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi4ELi0ELb1EEEvNS_10PassParamsE", 2 * 8 * 4),
-    "c5  score_units_kernel<R=8,C=4,SAT,profile>  (pipelined strips)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi4ELi1ELb1EEEvNS_10PassParamsE", 2 * 8 * 4),
-    "c5  score_units_kernel<R=4,C=4,EXACT,profile>  (pipelined strips, short references)": ("sw_inst_r4.o", "_ZN3swb18score_units_kernelILi4ELi4ELi0ELb1EEEvNS_10PassParamsE", 2 * 4 * 4),
+    "c5  score_units_kernel<R=4,C=8,EXACT,profile>  (pipelined strips)": ("sw_inst_r4.o", "_ZN3swb18score_units_kernelILi4ELi8ELi0ELb1EEEvNS_10PassParamsE", 2 * 4 * 8),
+    "c5  score_units_kernel<R=4,C=8,SAT,profile>  (pipelined strips)": ("sw_inst_r4.o", "_ZN3swb18score_units_kernelILi4ELi8ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 8),
+    "c5  score_units_kernel<R=8,C=8,EXACT,profile>  (pipelined strips, when the boundary rows of 4-row strips do not fit HBM)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi8ELi0ELb1EEEvNS_10PassParamsE", 2 * 8 * 8),
+    "c5  score_units_kernel<R=8,C=8,SAT,profile>  (pipelined strips, when the boundary rows of 4-row strips do not fit HBM)": ("sw_inst_r8.o", "_ZN3swb18score_units_kernelILi8ELi8ELi1ELb1EEEvNS_10PassParamsE", 2 * 8 * 8),
 }
+
+
+def registers(obj, kernel):
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", os.path.join(OBJ, obj)], capture_output=True, text=True, check=True).stdout
+    m = re.search(re.escape(kernel) + r":\s*\n\s*REG:(\d+)", out)
+    return int(m.group(1)) if m else None
 
 
 def loop_mix(obj, kernel, cell_pairs):
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", kernel, os.path.join(OBJ, obj)], capture_output=True, text=True, check=True).stdout
     ins = []
-    for line in sass.split("\n"):
+    lines = sass.split("\n")
+    for n, line in enumerate(lines):
         m = re.search(r"/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)(.*?);", line)
         if m:
-            ins.append((int(m.group(1), 16), m.group(2), m.group(3)))
+            # the second 64-bit word of the encoding carries the scheduler's stall count (bits 41..44 of that word)
+            hi = re.search(r"/\* (0x[0-9a-f]{16}) \*/", lines[n + 1]) if n + 1 < len(lines) else None
+            ins.append((int(m.group(1), 16), m.group(2), m.group(3), (int(hi.group(1), 16) >> 41) & 0xF if hi else 0))
     want = 2 * cell_pairs                       # at least two DPX instructions per cell pair (three in SAT_U8)
     best = None
-    for a, op, rest in ins:
+    for a, op, rest, _ in ins:
         if op == "BRA":
             m = re.search(r"0x([0-9a-f]+)", rest)
             if m and int(m.group(1), 16) < a:
@@ -65,7 +75,8 @@ def loop_mix(obj, kernel, cell_pairs):
     fma = sum(v for k, v in mix.items() if k in FMA)
     unknown = sorted(k for k in mix if k not in ALU and k not in FMA and k not in {"LDS", "LDG", "STG", "STS", "SHFL", "BRA", "LDC", "LDCU", "NANOSLEEP", "WARPSYNC", "BSSY", "BSYNC", "NOP",
                                                                                 "UMOV", "UIADD3", "ULEA", "UISETP", "ULOP3", "USEL", "UIMAD", "USHF", "R2UR", "S2R", "MEMBAR", "ATOMG", "LD", "ST", "CCTL", "ERRBAR", "VOTE", "UFLO", "UPOPC", "REDUX", "S2UR", "UPRMT", "UMNMX", "BAR", "YIELD", "CALL", "RET", "EXIT", "BMOV", "DEPBAR"})
-    return dict(object=obj, kernel=kernel, loop_instructions=len(best), cell_pairs_per_lane_per_trip=cell_pairs,
+    return dict(object=obj, kernel=kernel, registers=registers(obj, kernel), loop_instructions=len(best), scheduled_stall_cycles=sum(x[3] for x in best),
+                cell_pairs_per_lane_per_trip=cell_pairs,
                 alu_pipe_instructions=alu, fma_pipe_instructions=fma, alu_inst_per_cell_pair=round(alu / cell_pairs, 4),
                 inst_per_cell_pair=round(len(best) / cell_pairs, 4), mix=dict(mix.most_common()), unclassified=unknown)
 
@@ -77,7 +88,10 @@ def main():
         with open(OUT) as f:
             old = json.load(f)
         bad = [k for k in doc["kernels"] if old["kernels"].get(k, {}).get("alu_pipe_instructions") != doc["kernels"][k]["alu_pipe_instructions"]
-               or old["kernels"].get(k, {}).get("loop_instructions") != doc["kernels"][k]["loop_instructions"]]
+               or old["kernels"].get(k, {}).get("loop_instructions") != doc["kernels"][k]["loop_instructions"]
+               or old["kernels"].get(k, {}).get("registers") != doc["kernels"][k]["registers"]]
+        # occupancy guard: the batched score kernels must keep 4 blocks of 128 threads per SM
+        bad += [k + " (more than 128 registers)" for k, v in doc["kernels"].items() if " score_kernel<" in k and (v["registers"] or 999) > 128]
         if bad:
             print("stale:", bad)
             sys.exit(1)
@@ -86,7 +100,7 @@ def main():
     with open(OUT, "w") as f:
         json.dump(doc, f, indent=1)
     for k, v in doc["kernels"].items():
-        print(f"{k}\n    loop {v['loop_instructions']} instr, ALU pipe {v['alu_pipe_instructions']} = {v['alu_inst_per_cell_pair']} / cell pair, FMA pipe {v['fma_pipe_instructions']}, unclassified {v['unclassified']}")
+        print(f"{k}\n    {v['registers']} registers, loop {v['loop_instructions']} instr ({v['scheduled_stall_cycles']} scheduled cycles), ALU pipe {v['alu_pipe_instructions']} = {v['alu_inst_per_cell_pair']} / cell pair, FMA pipe {v['fma_pipe_instructions']}, unclassified {v['unclassified']}")
 
 
 if __name__ == "__main__":
