@@ -79,6 +79,30 @@ def gather_by_index(values, parts, group=None):
     return res
 
 
+def make_index_gather(parts, device, group=None):
+    """gather_by_index for MANY rounds over the same partition (a database search runs one round per query): the padded
+    receive buffer and the permutation back into entry order are built once, every round is one all-gather of the packed
+    (score, pos) words and one index_select on the device.  Returns fn(score_i32, pos_i32) -> (score_all, pos_all)."""
+    world = dist.get_world_size(group)
+    counts = [int(p.numel()) for p in parts]
+    mx = max(counts)
+    total = sum(counts)
+    src = torch.empty(total, dtype=torch.int64)          # position in the gathered buffer of every entry
+    for r, p in enumerate(parts):
+        src[p] = torch.arange(r * mx, r * mx + counts[r], dtype=torch.int64)
+    src = src.to(device)
+    pad = torch.zeros(mx, dtype=torch.int64, device=device)
+    out = torch.empty(world * mx, dtype=torch.int64, device=device)
+
+    def fn(score, pos):
+        n = score.numel()
+        pad[:n] = (score.to(torch.int64) << 32) | (pos.to(torch.int64) & 0xFFFFFFFF)
+        dist.all_gather_into_tensor(out, pad, group=group)
+        both = out.index_select(0, src)
+        return (both >> 32).to(torch.int32), (both & 0xFFFFFFFF).to(torch.int32)
+    return fn
+
+
 def reference_sharded_align(align_piece, reads, y, ratio, make_string_range, group=None, realign=None, device="cpu"):
     """Long-pair config: the REFERENCE is split over the ranks into `world` overlapping
     ranges with the reference's own rule (_make_string_range, plocalaligner.cpp:44-67: halo = floor(ratio * m)),

@@ -121,6 +121,10 @@ assert max(loads) - min(loads) <= int(lens.max())
 mine = parts[rank]
 vals = sh.gather_by_index((mine * 5 + 2).to(torch.int32), parts)
 assert vals.tolist() == [5 * i + 2 for i in range(333)], rank
+gather = sh.make_index_gather(parts, torch.device("cpu"))       # the per-query gather of a database search: built once
+for rnd in range(3):
+    s_g, p_g = gather((mine * 5 + rnd).to(torch.int32), (mine * 7 + 3).to(torch.int32))
+    assert s_g.tolist() == [5 * i + rnd for i in range(333)] and p_g.tolist() == [7 * i + 3 for i in range(333)], rank
 # long pairs: the reference split over the ranks, one all-reduce(max) picks the piece like the serial
 # OMPParallelLocalAligner(x, y, npiece = world, ratio) does (oracle as the stand-in aligner)
 sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
