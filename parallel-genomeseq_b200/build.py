@@ -22,12 +22,20 @@ def _run(cmd):
     subprocess.check_call(cmd)
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.isfile(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS + [__file__]):
-        return LIB
+def build(force=False, verbose=False, checked=False):
+    """checked=True: the same library with -DSWB_CHECKED (own bounds checks at every work-buffer store and pass-2 ring access,
+    see sw_core.cuh) as libswb200_checked.so — the stand-in for compute-sanitizer memcheck, run by a GPU test."""
+    global LIB, OBJ
+    if checked:
+        lib, obj = os.path.join(HERE, "libswb200_checked.so"), os.path.join(HERE, "build", "checked")
+    else:
+        lib, obj = os.path.join(HERE, "libswb200.so"), os.path.join(HERE, "build")
+    if not force and os.path.isfile(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in DEPS + [__file__]):
+        return lib
+    LIB, OBJ = lib, obj
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SWB_NVCC_EXTRA", "").split()
+    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SWB_NVCC_EXTRA", "").split() + (["-DSWB_CHECKED"] if checked else [])
     jobs = [[nvcc] + CFLAGS + extra + ["-c", os.path.join(CSRC, "swb200.cu"), "-o", os.path.join(OBJ, "swb200.o")]]
     for r in R_SET:
         jobs.append([nvcc] + CFLAGS + extra + [f"-DSWB_R={r}", "-c", os.path.join(CSRC, "sw_inst.cu"), "-o", os.path.join(OBJ, f"sw_inst_r{r}.o")])
@@ -39,4 +47,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, checked="--checked" in sys.argv))

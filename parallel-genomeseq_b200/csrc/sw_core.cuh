@@ -60,6 +60,15 @@ struct Scoring {
   int32_t G;
 };
 
+// Own bounds checks (-DSWB_CHECKED, libswb200_checked.so): compute-sanitizer is closed on the GPU pool this was built on, so
+// every store into a work buffer, every ring access of pass 2 and the unmasked reference loads carry an index check that
+// records a site code in PassParams::check (the host turns a non-zero code into an error).  Compiled out otherwise.
+#ifdef SWB_CHECKED
+#define SWB_CHECK(chk, cond, code) do { if (!(cond) && (chk)) atomicMax((chk), (uint32_t)(code)); } while (0)
+#else
+#define SWB_CHECK(chk, cond, code) do { } while (0)
+#endif
+
 struct PassParams {
   const uint8_t* ref_raw;      // y bytes
   const uint8_t* ref_code;     // y alphabet codes (profile select)
@@ -80,6 +89,8 @@ struct PassParams {
   uint32_t* abort_flag;        // set when a consumer gave up waiting (never expected; avoids a hang)
   uint32_t* ticket;            // units are handed out in the order in which warps actually start (score_units_kernel)
   int strips;                  // host: some pair of the class has more than one row strip (score_strips_kernel instead of score_kernel)
+  uint32_t* check;             // SWB_CHECKED builds: highest failing check site (0 = none), null otherwise
+  unsigned long long ck_words, blk_words, bnd_words, ref_len;   // sizes of the work buffers (for the checks)
   int L, logL, B, logB;
   Scoring sc;
 };
@@ -206,6 +217,7 @@ template <bool PROFILE, bool MASKED = true>
 __device__ __forceinline__ uint32_t load_y(const PassParams& p, const PairDesc& pd, int j) {
   if (!MASKED) {
     const uint32_t idx = pd.y_off + (uint32_t)(j - 1);
+    SWB_CHECK(p.check, j >= 1 && (unsigned long long)idx < p.ref_len, 1);
     if (PROFILE) return __ldg(p.ref_code + idx);
     return SYM_BASE | __ldg(p.ref_raw + idx);
   }
@@ -412,6 +424,7 @@ struct Wavefront {
       for (int c = 0; c < C; ++c) {
         const int j = col_of<C>(t, g, c);
         if (bnd_out && g == L - 1 && j >= 1 && j <= (int)pd.n) {
+          SWB_CHECK(p.check, pd.bnd_off + (unsigned long long)strip * (pd.n + 1) + j < p.bnd_words, 6);
           bnd_out[j] = st.bot[c];
           if (publish_to && ((j & 511) == 0 || j == (int)pd.n)) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)j; }
         }
@@ -538,6 +551,8 @@ __device__ __forceinline__ void score_pass(Wavefront<R, C, AM, PROFILE>& wf, con
     else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps<true, BND>(pd, t, bmax, nohook); }
     const uint32_t gm = group_max_s16x2<AM == AM_WIDE>(bmax, L);
     if (live && b < (int)pd.nblk) {
+      SWB_CHECK(p.check, pd.blk_off + wf.blk_index(pd, b) < p.blk_words, 2);
+      SWB_CHECK(p.check, (pd.ck_off + wf.ck_index(pd, b) + (unsigned long long)state_words<R, C, AM>() * L <= p.ck_words), 3);
       if (g == 0) blk[wf.blk_index(pd, b)] = gm;
       save_state<R, C, AM>(wf.st, p.sc, ck + wf.ck_index(pd, b), L, g);
     }
@@ -638,7 +653,10 @@ struct UnitsWavefront : Wavefront<R, C, AM, PROFILE> {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = col_of<C>(t, this->lane, c);
-      if (writer && (!MASKED || (j >= 1 && j <= (int)pd.n))) this->bnd_out[j] = this->st.bot[c];
+      if (writer && (!MASKED || (j >= 1 && j <= (int)pd.n))) {
+        SWB_CHECK(this->p.check, j >= 1 && j <= (int)pd.n && pd.bnd_off + (unsigned long long)this->strip * (pd.n + 1) + j < this->p.bnd_words, 7);
+        this->bnd_out[j] = this->st.bot[c];
+      }
     }
   }
   // steps t and t+1, software-pipelined like Wavefront::two_steps
@@ -709,6 +727,8 @@ __global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
     if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<false>(pd, t, bmax); }
     else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<true>(pd, t, bmax); }
     const uint32_t gm = group_max_s16x2<AM == AM_WIDE>(bmax, 32);
+    SWB_CHECK(p.check, pd.blk_off + wf.blk_index(pd, b) < p.blk_words, 4);
+    SWB_CHECK(p.check, (pd.ck_off + wf.ck_index(pd, b) + (unsigned long long)state_words<R, C, AM>() * 32 <= p.ck_words), 5);
     if (lane == 0) blk[wf.blk_index(pd, b)] = gm;
     save_state<R, C, AM>(wf.st, p.sc, ck + wf.ck_index(pd, b), 32, lane);
     bmax = NEG_INF2;
@@ -744,6 +764,7 @@ struct TraceParams {
   int NB;                     // band: lanes per group kept in the ring (the lane of the current row and NB-1 above it)
   int nlc;                    // local checkpoint slots per warp (power of two)
   int ring_off;               // word offset of the rings in dynamic shared memory (after the profiles)
+  unsigned long long scratch_words;   // size of scratch (for the SWB_CHECKED bounds checks)
   int32_t* out_score;
   uint32_t* out_pos;
   uint32_t* out_end;          // 2 per task: index_x, index_y of the arg-max
@@ -1008,6 +1029,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
           for (int c = 0; c < C; ++c) {
             const uint32_t* v = C == 1 ? wf.st.E : colv[c];
             uint32_t* dst = ring_lane + ((col_of<C>(t, g, c) - 1) & cmask) * cstride;
+            SWB_CHECK(p.check, g - band_lo >= 0 && g - band_lo < NB && (dst - ring) + PW <= (cmask + 1) * cstride, 8);
             if (SAT) {
 #pragma unroll
               for (int w = 0; w < PW; ++w) {                   // four rows per word: the low byte of the half (E mod 256)
@@ -1025,7 +1047,10 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
             }
           }
         }
-        if (on && (t & wmask) == 0) save_state<R, C, AM>(wf.st, p.sc, lck + (size_t)((t >> tp.logWc) & (tp.nlc - 1)) * SW * 32, 32, lane);
+        if (on && (t & wmask) == 0) {
+          SWB_CHECK(p.check, (size_t)gwarp * tp.nlc * SW * 32 + (size_t)((t >> tp.logWc) & (tp.nlc - 1)) * SW * 32 + SW * 32 <= tp.scratch_words, 9);
+          save_state<R, C, AM>(wf.st, p.sc, lck + (size_t)((t >> tp.logWc) & (tp.nlc - 1)) * SW * 32, 32, lane);
+        }
       });
       wf.restore_from = nullptr;
       if (!done) {
@@ -1056,6 +1081,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
           const int r = i - i_min;
           const int e = (RP == R) ? r : r + (r / R) * (RP - R);          // rows of a lane are padded to whole words
           const int col = ((j - 1) & cmask) * cstride;
+          SWB_CHECK(p.check, r >= 0 && e >= 0 && e < NB * RP && j >= 1, 10);
           if (SAT) return (int)((reinterpret_cast<const uint8_t*>(ring)[col * 4 + e] + (uint32_t)G) & 0xFFu);
           if (WIDE) return (int)ring[col + e] + G;
           return (int)reinterpret_cast<const int16_t*>(ring)[col * 2 + e] + G;
@@ -1083,6 +1109,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
           const bool emit = tp.want_consensus && len < tp.cons_cap;
           if (len >= tp.cons_cap) flags |= 1u;               // consensus truncated; the walk goes on, so pos stays exact
           uint8_t xc = 0, yc = 0;
+          SWB_CHECK(p.check, ix >= 1 && iy >= 1 && ix <= m && iy <= n && (!emit || len < tp.cons_cap), 11);
           if (emit) { xc = xraw[ix - 1]; yc = yraw[iy - 1]; }
           const uint8_t rx = QS ? yc : xc, ry = QS ? xc : yc;   // the reference's x / y characters of this cell
           if (n1 == 0 || n2 == 0 || n3 == 0) {

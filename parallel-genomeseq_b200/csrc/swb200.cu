@@ -107,6 +107,7 @@ struct swb_ctx {
   std::vector<LaunchClass> classes;
   DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
+  DevBuf d_check;                     // SWB_CHECKED builds: one word, the highest failing bounds-check site
   // query-stationary mode (sw_qs.cuh): database search against a short reference, computed transposed
   bool qs = false;
   int qs_KP = 0;
@@ -519,6 +520,8 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     pp.bnd = ctx->d_bnd.as<uint32_t>();
     pp.L = L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
     pp.strips = lc.max_strips > 1 ? 1 : 0;
+    pp.check = ctx->d_check.as<uint32_t>();
+    pp.ck_words = lc.ck_words; pp.blk_words = lc.blk_words; pp.bnd_words = lc.bnd_words + 64; pp.ref_len = ctx->y.size();
     pp.sc = device_scoring(hs, force_default, wide);
     if (profile) pp.sc.G = hs.G;
 
@@ -621,6 +624,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
     CUDA_TRY(ctx->d_scratch.ensure((size_t)grid * warps_per_cta * tg.scratch_words * 4));
     tp.scratch = ctx->d_scratch.as<uint32_t>();
+    tp.scratch_words = (unsigned long long)grid * warps_per_cta * tg.scratch_words;
     tp.out_score = ctx->d_score.as<int32_t>();
     tp.out_pos = ctx->d_pos.as<uint32_t>();
     tp.out_end = ctx->d_end.as<uint32_t>();
@@ -806,6 +810,8 @@ int run_qs(swb_ctx* ctx) {
     pp.L = L; pp.logL = lc.geo.logL; pp.B = ctx->B; pp.logB = ctx->logB;
     pp.sc = device_scoring(hs, false);
     pp.sc.G = hs.G;
+    pp.check = ctx->d_check.as<uint32_t>();
+    pp.ck_words = lc.ck_words; pp.blk_words = lc.blk_words; pp.bnd_words = 0; pp.ref_len = ctx->batch_residues;
     qp.m = (int)ctx->y.size();
     const size_t smem = (size_t)ctx->qs_KP * R * 32 * 4;      // score pass: 32-bit profile, one per thread block
     const size_t smem_trace = smem / 2;                       // pass 2: 16-bit profile
@@ -839,6 +845,7 @@ int run_qs(swb_ctx* ctx) {
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
     CUDA_TRY(ctx->d_scratch.ensure((size_t)grid * warps_per_cta * tg.scratch_words * 4));
     tp.scratch = ctx->d_scratch.as<uint32_t>();
+    tp.scratch_words = (unsigned long long)grid * warps_per_cta * tg.scratch_words;
     tp.out_score = ctx->d_score.as<int32_t>();
     tp.out_pos = ctx->d_pos.as<uint32_t>();
     tp.out_end = ctx->d_end.as<uint32_t>();
@@ -879,7 +886,11 @@ int run_qs(swb_ctx* ctx) {
 // =========================================================================================================
 extern "C" {
 
-const char* swb_version(void) { return "swb200 0.1 (sm_100a)"; }
+#ifdef SWB_CHECKED
+const char* swb_version(void) { return "swb200 0.2 (sm_100a, SWB_CHECKED bounds checks)"; }
+#else
+const char* swb_version(void) { return "swb200 0.2 (sm_100a)"; }
+#endif
 
 int swb_device_count(void) {
   int ndev = 0;
@@ -907,7 +918,7 @@ void swb_destroy(swb_ctx* ctx) {
   free_classes(ctx->classes);
   for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd, &ctx->d_units, &ctx->d_progress,
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
-                    &ctx->d_len, &ctx->d_flags, &ctx->d_xcode, &ctx->d_qs_table}) b->release();
+                    &ctx->d_len, &ctx->d_flags, &ctx->d_xcode, &ctx->d_qs_table, &ctx->d_check}) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1164,6 +1175,10 @@ int swb_batch_run(swb_ctx* ctx, float* device_us) {
   ctx->stats.cells_reference = cells_ref;
   const bool chunked = ctx->npiece >= 1;
   const bool realign = chunked && !ctx->sc.is_default();
+#ifdef SWB_CHECKED
+  CUDA_TRY(ctx->d_check.ensure(4));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_check.p, 0, 4, ctx->stream));
+#endif
   CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
   ctx->ev_used = 0;
   if (ctx->qs) {
@@ -1201,6 +1216,13 @@ int swb_batch_run(swb_ctx* ctx, float* device_us) {
   CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(cudaGetLastError());
+#ifdef SWB_CHECKED
+  {
+    uint32_t site = 0;
+    CUDA_TRY(cudaMemcpy(&site, ctx->d_check.p, 4, cudaMemcpyDeviceToHost));
+    if (site) return fail(ctx, SWB_ERR_CUDA, "SWB_CHECKED: bounds check failed at site " + std::to_string(site));
+  }
+#endif
   float ms = 0, ms2 = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) { float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1])); ms2 += t; }

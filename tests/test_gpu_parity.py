@@ -711,3 +711,23 @@ def test_rebind_reference_keeps_the_database_resident(engine, pkg):
     with pytest.raises(pkg.SwbError) as ei:
         engine.rebind_reference("ACGT" * 100)
     assert ei.value.code == -6
+
+
+def test_checked_build_runs_clean():
+    """libswb200_checked.so = the same sources with -DSWB_CHECKED: every store into a work buffer (checkpoints, block maxima,
+    strip boundary rows, local checkpoints), every access of the pass-2 ring and the unmasked reference loads carry an index
+    check that turns into an error code.  compute-sanitizer is closed on the GPU pool (profiles/sanitizer_r02_closed.txt);
+    this is the stand-in for its memcheck: a batch through every kernel family and a fuzz run must pass with no check firing."""
+    import os
+    import subprocess
+    import sys as _sys
+    from conftest import ROOT
+    lib = os.path.join(ROOT, "parallel-genomeseq_b200", "libswb200_checked.so")
+    if not os.path.isfile(lib):
+        subprocess.check_call([_sys.executable, os.path.join(ROOT, "parallel-genomeseq_b200", "build.py"), "--checked"])
+    env = {k: v for k, v in os.environ.items() if not k.startswith("SWB_")}
+    env["SWB_LIB_PATH"] = lib
+    r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "sanitize case ok" in r.stdout and "SWB_CHECKED" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "150", "4711"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout + r.stderr

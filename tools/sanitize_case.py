@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""A small batch through every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck): batched
+"""A small batch through every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck) and for the
+SWB_CHECKED build of the library (own bounds checks; SWB_LIB_PATH=parallel-genomeseq_b200/libswb200_checked.so): batched
 kernels (both arithmetic modes, chunked), row strips run by one warp, pipelined strips (warps synchronising through HBM
 flags), the query-stationary kernels, wide lanes and the dense-matrix replay.  Sizes are tiny: the tools slow kernels
 down by one to two orders of magnitude.  Results are checked against the oracle so that a clean log means a clean RUN.
@@ -67,7 +68,7 @@ def main():
     eng.set_reference("TGTTACGG")
     assert (eng.matrix("GGTTGACTA") == o.matrix("GGTTGACTA", "TGTTACGG")).all()
     eng.close()
-    print("sanitize case ok")
+    print("sanitize case ok:", pkg.load_library().swb_version().decode())
 
 
 if __name__ == "__main__":
