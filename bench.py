@@ -667,6 +667,16 @@ def main():
         e2e_t.append(time.perf_counter() - t0)
     barrier()
     assert (out["score"] == res["score"]).all() and (out["pos"] == res["pos"]).all()
+    # where the end-to-end time goes: the same call in its three parts (one extra, untimed-for-e2e iteration)
+    t0 = time.perf_counter()
+    eng.stage((blob_np, offs_np), consensus=True, cons_stride=cons_stride)
+    t1 = time.perf_counter()
+    eng.run()
+    t2 = time.perf_counter()
+    eng.fetch()
+    t3 = time.perf_counter()
+    e2e_parts = {"stage_ms": (t1 - t0) * 1e3, "run_ms": (t2 - t1) * 1e3, "fetch_ms": (t3 - t2) * 1e3,
+                 "note": "swb_batch_stage (host preparation + H2D) / swb_batch_run (kernels) / swb_batch_fetch (D2H into fresh host arrays)"}
 
     # ---- reduce over ranks: max time, sum of work ------------------------------------------------------------
     step_us = float(np.mean(dev_us))
@@ -704,7 +714,7 @@ def main():
                        "reads_per_gpu_per_step": n_reads, "cells_per_step_per_gpu": cells_step, "parallelism": f"reads sharded over {world} GPU(s), reference replicated, one NCCL all-gather of (score,pos)",
                        "l2": "flushed (256 MiB write) between timed iterations; per-step work buffers (checkpoints) exceed L2",
                        "geometry": {"lanes_per_pair": st["lanes_per_pair"], "rows_per_lane": st["rows_per_lane"], "block_steps": st["block_steps"]}},
-            "e2e": {"value": e2e_gcups, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+            "e2e": {"value": e2e_gcups, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "parts": e2e_parts},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

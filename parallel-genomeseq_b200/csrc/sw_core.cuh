@@ -491,6 +491,7 @@ struct Wavefront {
     uint32_t yq[DEPTH][C];
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) load_symbols_m<true>(pd, t0 + 1 + d, yq[d]);
+#pragma unroll 2
     for (int s = 1; s <= nsteps; ++s) {
       const int t = t0 + s;
       uint32_t ycur[C];
