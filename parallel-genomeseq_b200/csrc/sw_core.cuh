@@ -491,7 +491,6 @@ struct Wavefront {
     uint32_t yq[DEPTH][C];
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) load_symbols_m<true>(pd, t0 + 1 + d, yq[d]);
-#pragma unroll 2
     for (int s = 1; s <= nsteps; ++s) {
       const int t = t0 + s;
       uint32_t ycur[C];
@@ -1082,7 +1081,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
           const int r = i - i_min;
           const int e = (RP == R) ? r : r + (r / R) * (RP - R);          // rows of a lane are padded to whole words
           const int col = ((j - 1) & cmask) * cstride;
-          SWB_CHECK(p.check, r >= 0 && e >= 0 && e < NB * RP && j >= 1, 10);
+          SWB_CHECK(p.check, r >= 0 && e >= 0 && e < NB * RP && j >= j_min_of(i), 10);   // j may be 0: a stored virtual column (H = 0)
           if (SAT) return (int)((reinterpret_cast<const uint8_t*>(ring)[col * 4 + e] + (uint32_t)G) & 0xFFu);
           if (WIDE) return (int)ring[col + e] + G;
           return (int)reinterpret_cast<const int16_t*>(ring)[col * 2 + e] + G;

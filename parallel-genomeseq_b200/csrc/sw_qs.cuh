@@ -116,7 +116,6 @@ struct QsWavefront {
     uint32_t qa[DEPTH], qb[DEPTH];
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) load_codes<true>(pd, t0 + 1 + d, qa[d], qb[d]);
-#pragma unroll 2
     for (int s = 1; s <= nsteps; ++s) {
       const int t = t0 + s;
       const uint32_t ca = qa[0], cb = qb[0];
