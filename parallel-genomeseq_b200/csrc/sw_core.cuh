@@ -87,7 +87,10 @@ struct PassParams {
   int nunits;
   uint32_t* progress;          // per unit: boundary columns published so far
   uint32_t* abort_flag;        // set when a consumer gave up waiting (never expected; avoids a hang)
-  uint32_t* ticket;            // units are handed out in the order in which warps actually start (score_units_kernel)
+  uint32_t* ticket;            // tasks are handed out in the order in which warps ask for them (score_units_kernel)
+  uint32_t* blocks_done;       // per unit: tasks finished so far
+  int task_blocks;             // checkpoint blocks per task
+  uint32_t ntickets;           // rounds * nunits
   int strips;                  // host: some pair of the class has more than one row strip (score_strips_kernel instead of score_kernel)
   uint32_t* check;             // SWB_CHECKED builds: highest failing check site (0 = none), null otherwise
   unsigned long long ck_words, blk_words, bnd_words, ref_len;   // sizes of the work buffers (for the checks)
@@ -157,13 +160,20 @@ struct CompareSelect {
   }
 };
 
-// Profile selection: per-warp query profile in shared memory, word index ((code*R + k)*32 + lane).
-template <int R, int C>
+// Rows per lane padded for 128-bit profile loads (VEC layout below): a multiple of 4 words that is 4 mod 8, so that the
+// 8 lanes of a quarter warp — one LDS.128 wavefront — hit 32 distinct banks.
+template <int R> __host__ __device__ constexpr int prof_stride() { return ((R + 3) / 4 * 4) % 8 == 4 ? (R + 3) / 4 * 4 : (R + 3) / 4 * 4 + 4; }
+
+// Profile selection: per-warp query profile in shared memory.
+//   scalar layout (pass 2, dense dump): word (code*R + k)*32 + lane — bank = lane, one LDS per cell pair;
+//   VEC layout (the score kernels): word (code*32 + lane)*S + k, S = prof_stride<R>() — the R scores of a lane's rows for
+//   one column symbol are contiguous and fetched four rows per LDS.128 into registers (RegSelect::fetch).
+template <int R, int C, bool VEC = false>
 struct ProfileSelect {
-  const uint32_t* prof;   // shared memory, already offset by lane
+  const uint32_t* prof;   // shared memory, already offset by lane (VEC: by lane * S)
   const uint32_t* col[C];
-  __device__ __forceinline__ void set_column(int c, uint32_t ycode) { col[c] = prof + ycode * (R * 32); }
-  __device__ __forceinline__ uint32_t operator()(int k, int c) const { return col[c][k * 32]; }
+  __device__ __forceinline__ void set_column(int c, uint32_t ycode) { col[c] = prof + ycode * ((VEC ? prof_stride<R>() : R) * 32); }
+  __device__ __forceinline__ uint32_t operator()(int k, int c) const { return VEC ? col[c][k] : col[c][k * 32]; }
 };
 
 // One wavefront step for one lane: C columns of rows [g*R, (g+1)*R).  The C column chains are independent
@@ -240,6 +250,21 @@ struct RegSelect {
 #pragma unroll
       for (int c = 0; c < C; ++c) s[k][c] = sel(k, c);
   }
+  // VEC profile: four rows per LDS.128
+  __device__ __forceinline__ void fetch(const ProfileSelect<R, C, true>& sel) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint4* q = reinterpret_cast<const uint4*>(sel.col[c]);
+#pragma unroll
+      for (int k4 = 0; k4 < (R + 3) / 4; ++k4) {
+        const uint4 v = q[k4];
+        s[4 * k4][c] = v.x;
+        if (4 * k4 + 1 < R) s[4 * k4 + 1][c] = v.y;
+        if (4 * k4 + 2 < R) s[4 * k4 + 2][c] = v.z;
+        if (4 * k4 + 3 < R) s[4 * k4 + 3][c] = v.w;
+      }
+    }
+  }
 };
 
 template <int R, int C>
@@ -303,7 +328,7 @@ __device__ __forceinline__ void load_compare_rows(CompareSelect<R, C, WIDE>& sel
 }
 
 // Build this lane's slice of the per-warp profile: prof[(code*R + k)*32 + lane] = pack(T[xA][code], T[xB][code]).
-template <int R, bool WIDE = false>
+template <int R, bool WIDE = false, bool VEC = false>
 __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassParams& p, const PairDesc& pd, int g, int lane) {
   const uint32_t* q = p.qpairs + pd.q_off + (uint32_t)g * R;
   for (int k = 0; k < R; ++k) {
@@ -313,7 +338,7 @@ __device__ __forceinline__ void build_profile(uint32_t* prof_warp, const PassPar
       // sentinel rows (a/b >= 256) and the sentinel column use the table's last row/column: never a match
       const int16_t sa = p.table[(a < 256 ? a : 256) * p.KP + c];
       const int16_t sb = p.table[(b < 256 ? b : 256) * p.KP + c];
-      prof_warp[(c * R + k) * 32 + lane] = WIDE ? (uint32_t)(int32_t)sa : ((uint32_t)(uint16_t)sa | ((uint32_t)(uint16_t)sb << 16));
+      prof_warp[VEC ? (c * 32 + lane) * prof_stride<R>() + k : (c * R + k) * 32 + lane] = WIDE ? (uint32_t)(int32_t)sa : ((uint32_t)(uint16_t)sa | ((uint32_t)(uint16_t)sb << 16));
     }
   }
 }
@@ -332,12 +357,13 @@ __device__ __forceinline__ uint32_t group_max_s16x2(uint32_t v, int L) {
 // Strips run top to bottom; the last row of strip s is written to a boundary row in HBM (one packed word
 // per column) and read back as the "north" input of strip s+1 — 32 columns per coalesced load, handed to
 // lane 0 with one shuffle per step.  BND selects that code path (compiled out for single-strip launches).
-template <int R, int C, int AM, bool PROFILE>
+template <int R, int C, int AM, bool PROFILE, bool VEC = false>
 struct Wavefront {
   static constexpr bool SAT = AM == AM_SAT, WIDE = AM == AM_WIDE;
+  static constexpr int PROF_ROWS = VEC ? prof_stride<R>() : R;     // profile words per (symbol, lane)
   const PassParams& p;
   CompareSelect<R, C, WIDE> csel;
-  ProfileSelect<R, C> psel;
+  ProfileSelect<R, C, VEC> psel;
   LaneState<R, C> st;
   int L, g, lane;
   int strip = 0;
@@ -360,8 +386,8 @@ struct Wavefront {
     PairDesc sp = pd;
     sp.q_off = pd.q_off + (uint32_t)s * (uint32_t)(L * R);
     if (PROFILE) {
-      build_profile<R, WIDE>(prof_warp, p, sp, g, lane);     // every lane fills (and later reads) only its own column
-      psel.prof = prof_warp + lane;
+      build_profile<R, WIDE, VEC>(prof_warp, p, sp, g, lane);     // every lane fills (and later reads) only its own column
+      psel.prof = prof_warp + (VEC ? lane * prof_stride<R>() : lane);
     } else {
       load_compare_rows<R, C>(csel, p, sp, g);
     }
@@ -534,8 +560,8 @@ struct Wavefront {
 // Pass 1: score pass.  One group of L lanes per pair, 32/L pairs per warp (or one warp per strip).
 // Blocks whose columns (plus the two-step look-ahead) are inside [1, n] for every lane skip the range tests.
 // ======================================================================================================
-template <int R, int C, int AM, bool PROFILE, bool BND>
-__device__ __forceinline__ void score_pass(Wavefront<R, C, AM, PROFILE>& wf, const PassParams& p, const PairDesc& pd,
+template <int R, int C, int AM, bool PROFILE, bool BND, class WF>
+__device__ __forceinline__ void score_pass(WF& wf, const PassParams& p, const PairDesc& pd,
                                            int steps, int n_min, bool live) {
   const int L = wf.L, g = wf.g;
   uint32_t* blk = p.blkmax + pd.blk_off;
@@ -578,13 +604,13 @@ __device__ __forceinline__ void score_batched(const PassParams& p, uint32_t* sme
   const int L = p.L;
   const int g = lane & (L - 1);
   const int groups_per_warp = 32 >> p.logL;
-  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
+  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * prof_stride<R>() * 32;
   int pair = gwarp * groups_per_warp + (lane >> p.logL);
   const bool live = pair < p.npairs;
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
   const PairDesc pd = p.pairs[pair];
 
-  Wavefront<R, C, AM, PROFILE> wf(p);
+  Wavefront<R, C, AM, PROFILE, true> wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
 
   // run whole blocks so that every lane flushes together; lanes past their range see sentinel columns
@@ -620,10 +646,10 @@ __global__ void __launch_bounds__(128) score_strips_kernel(const PassParams p) {
 }
 
 // ======================================================================================================
-// Pipelined strips (few long pairs): one warp per (pair, strip) unit, the strips of a pair run concurrently.
+// Pipelined strips (few long pairs): the strips of a pair run concurrently, each some columns behind the strip above.
 // A strip reads the boundary row of the strip above as soon as that strip has published it (progress
-// counters), 32 columns per coalesced load.  Producers have lower unit indices than their consumers, and units are
-// handed out by an atomic ticket in the order in which warps start, so a waiting strip's producer is always resident.
+// counters), 32 columns per coalesced load.  The work is cut into tasks — (pair, strip) unit x a few checkpoint
+// blocks — that persistent warps, one per SM sub-partition, take from an atomic ticket (score_units_kernel below).
 //
 // This path has a kernel and a stepping routine of its own (UnitsWavefront adds to Wavefront, it changes
 // nothing in it): ptxas allocates registers and schedules per kernel, and the batched kernel above is
@@ -632,8 +658,8 @@ __global__ void __launch_bounds__(128) score_strips_kernel(const PassParams p) {
 // interior blocks, and progress is published once per few blocks instead of being tested per column.
 // ======================================================================================================
 template <int R, int C, int AM, bool PROFILE>
-struct UnitsWavefront : Wavefront<R, C, AM, PROFILE> {
-  using Base = Wavefront<R, C, AM, PROFILE>;
+struct UnitsWavefront : Wavefront<R, C, AM, PROFILE, true> {
+  using Base = Wavefront<R, C, AM, PROFILE, true>;
   bool writer = false;     // lane 31 of a strip that has a strip below it
   uint32_t chunk_next2 = 0;   // boundary chunks are fetched TWO chunks (64 columns) ahead of their use
   __device__ __forceinline__ UnitsWavefront(const PassParams& p_) : Base(p_) {}
@@ -690,52 +716,80 @@ struct UnitsWavefront : Wavefront<R, C, AM, PROFILE> {
 };
 
 template <int R, int C, int AM, bool PROFILE>
-__global__ void __launch_bounds__(128) score_units_kernel(const PassParams p) {
+__global__ void __launch_bounds__(32, 1) score_units_kernel(const PassParams p) {
   extern __shared__ uint32_t smem_prof[];
   const int lane = threadIdx.x & 31;
-  const int warp_in_cta = threadIdx.x >> 5;
-  uint32_t* prof_warp = smem_prof + (size_t)warp_in_cta * p.KP * R * 32;
-  // Atomic ticket: a warp takes the next unit when it STARTS, so the producer of its unit (the unit before it) is
-  // always resident already and forward progress never depends on the order in which thread blocks are dispatched.
-  int gwarp = 0;
-  if (lane == 0) gwarp = (int)atomicAdd(p.ticket, 1u);
-  gwarp = __shfl_sync(0xffffffffu, gwarp, 0);
-  if (gwarp >= p.nunits) return;
-  const uint2 u = p.units[gwarp];
-  const PairDesc pd = p.pairs[u.x];
+  uint32_t* prof_warp = smem_prof;                 // one warp per thread block
   UnitsWavefront<R, C, AM, PROFILE> wf(p);
   wf.L = 32; wf.g = lane; wf.lane = lane;
-  wf.prepare(pd, (int)u.y, prof_warp);
-  wf.writer = wf.bnd_out != nullptr && lane == 31;
-  wf.wait_on = u.y > 0 ? p.progress + (gwarp - 1) : nullptr;
-  uint32_t* const publish_to = (u.y + 1 < pd.nstrips) ? p.progress + gwarp : nullptr;   // wf.publish_to stays null: no per-column publishing
-
-  uint32_t* blk = p.blkmax + pd.blk_off;
-  uint32_t* ck = p.ckpt + pd.ck_off;
-  const int n = (int)pd.n;
-  const int nb = (int)pd.nblk;
-  // publishing costs a fence, waiting for it costs pipeline lag down the chain of strips: balance the two
-  // (a fence per block is nothing once a block is a few hundred steps; finer progress lets the strips below absorb jitter)
-  const int pub_every = p.B >= 256 ? 1 : max(1, min(16, (int)sqrtf(0.1f * (float)nb / (float)max(1u, pd.nstrips))));
-  int since_pub = 0;
-  wf.template begin<true>(pd, 0);
-  wf.chunk_next2 = wf.load_chunk(pd, 1);
-  uint32_t bmax = NEG_INF2;
-  for (int b = 0; b < nb; ++b) {
-    const int t0 = b << p.logB;
-    const bool interior = (t0 + 1 >= 32) && ((t0 + p.B + 2) * C <= n);
-    if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<false>(pd, t, bmax); }
-    else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<true>(pd, t, bmax); }
-    const uint32_t gm = group_max_s16x2<AM == AM_WIDE>(bmax, 32);
-    SWB_CHECK(p.check, pd.blk_off + wf.blk_index(pd, b) < p.blk_words, 4);
-    SWB_CHECK(p.check, (pd.ck_off + wf.ck_index(pd, b) + (unsigned long long)state_words<R, C, AM>() * 32 <= p.ck_words), 5);
-    if (lane == 0) blk[wf.blk_index(pd, b)] = gm;
-    save_state<R, C, AM>(wf.st, p.sc, ck + wf.ck_index(pd, b), 32, lane);
-    bmax = NEG_INF2;
-    if (publish_to && (++since_pub >= pub_every || b == nb - 1)) {
-      since_pub = 0;
-      const int jd = min(n, col_of<C>(t0 + p.B, 31, C - 1));    // last column lane 31 has finished
-      if (lane == 31 && jd >= 1) { __threadfence(); *(volatile uint32_t*)publish_to = (uint32_t)jd; }
+  int cur_unit = -1;
+  // Persistent warps, one per SM sub-partition, work through TASKS = (unit, task_blocks checkpoint blocks) handed out by
+  // an atomic ticket in round-major order: ticket = round * nunits + unit, task block = round - 2 * strip.  A task reads
+  // what (strip, block-1) wrote (checkpoint), the boundary row (strip-1, block) wrote and, in its last few dozen steps,
+  // the first columns of (strip-1, block+1): all three belong to earlier ROUNDS.  Tickets are taken in order, so whatever
+  // a task could wait for is finished or running (forward progress never depends on the dispatch order of thread
+  // blocks), and with no more warps than units per round it is normally finished: nobody polls in the steady state, and
+  // a slow SM delays nobody — it simply takes fewer tickets.  (One warp per strip for the whole pass, the round-1
+  // design, made every strip of a pair run at the pace of the slowest warp above it: 25 % of all issue slots of the
+  // 10 kbp x 51 Mbp run went into polling, profiles/score_units_kernel_r02_c5_ncu.txt.)
+  for (;;) {
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= p.ntickets) break;
+    const int unit = (int)(ticket % (uint32_t)p.nunits);
+    const int round = (int)(ticket / (uint32_t)p.nunits);
+    const uint2 u = p.units[unit];
+    const int tb = round - 2 * (int)u.y;                         // task block of this unit in this round
+    const PairDesc pd = p.pairs[u.x];
+    const int nb = (int)pd.nblk;
+    if (tb < 0 || tb * p.task_blocks >= nb) continue;
+    if (unit != cur_unit) {
+      cur_unit = unit;
+      wf.prepare(pd, (int)u.y, prof_warp);
+      wf.writer = wf.bnd_out != nullptr && lane == 31;
+      wf.wait_on = u.y > 0 ? p.progress + (unit - 1) : nullptr;   // units of a pair are consecutive, strips ascending
+      wf.seen_progress = 0;
+    }
+    volatile uint32_t* const done = p.blocks_done + unit;
+    if (tb > 0) {                                                 // this strip's previous task (checkpoint + boundary row position)
+      unsigned spins = 0;
+      while (*done < (uint32_t)tb) {
+        __nanosleep(200);
+        if (++spins > (1u << 24)) { if (p.abort_flag) *p.abort_flag = 1u; break; }
+      }
+      __threadfence();
+    }
+    uint32_t* const publish_to = (u.y + 1 < pd.nstrips) ? p.progress + unit : nullptr;   // wf.publish_to stays null: no per-column publishing
+    uint32_t* blk = p.blkmax + pd.blk_off;
+    uint32_t* ck = p.ckpt + pd.ck_off;
+    const int n = (int)pd.n;
+    const int b0 = tb * p.task_blocks, b1 = min(nb, b0 + p.task_blocks);
+    wf.template begin<true>(pd, b0 << p.logB);
+    wf.chunk_next2 = wf.load_chunk(pd, ((C * (b0 << p.logB)) >> 5) + 1);
+    uint32_t bmax = NEG_INF2;
+    for (int b = b0; b < b1; ++b) {
+      const int t0 = b << p.logB;
+      const bool interior = (t0 + 1 >= 32) && ((t0 + p.B + 2) * C <= n);
+      if (interior) { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<false>(pd, t, bmax); }
+      else { for (int t = t0 + 1; t <= t0 + p.B; t += 2) wf.template two_steps_units<true>(pd, t, bmax); }
+      const uint32_t gm = group_max_s16x2<AM == AM_WIDE>(bmax, 32);
+      SWB_CHECK(p.check, pd.blk_off + wf.blk_index(pd, b) < p.blk_words, 4);
+      SWB_CHECK(p.check, (pd.ck_off + wf.ck_index(pd, b) + (unsigned long long)state_words<R, C, AM>() * 32 <= p.ck_words), 5);
+      if (lane == 0) blk[wf.blk_index(pd, b)] = gm;
+      save_state<R, C, AM>(wf.st, p.sc, ck + wf.ck_index(pd, b), 32, lane);
+      bmax = NEG_INF2;
+      if (b == b1 - 1) {
+        // end of the task: every lane fences its own stores (boundary row: lane 31, checkpoints: all lanes), then one lane
+        // publishes the boundary columns finished so far (for the strip below) and the task count (for this strip's next task)
+        __threadfence();
+        __syncwarp();
+        if (lane == 31) {
+          const int jd = min(n, col_of<C>(t0 + p.B, 31, C - 1));    // last column lane 31 has finished
+          if (publish_to && jd >= 1) *(volatile uint32_t*)publish_to = (uint32_t)jd;
+          *done = (uint32_t)(tb + 1);
+        }
+      }
     }
   }
 }

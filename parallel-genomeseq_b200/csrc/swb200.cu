@@ -84,6 +84,7 @@ struct HostScoring {
 
 struct swb_ctx {
   int device = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
@@ -308,13 +309,22 @@ int upload_profile_table(swb_ctx* ctx) {
   return SWB_OK;
 }
 
+// Profile words per (symbol, lane) of the score kernels' 128-bit layout: prof_stride<R>() of sw_core.cuh.
+int prof_stride_rows(int R) { const int s = (R + 3) / 4 * 4; return s % 8 == 4 ? s : s + 4; }
+// Largest rows-per-lane whose per-warp score profile (KP symbols) fits `bytes` of shared memory.
+int max_rows_for_profile(int KP, size_t bytes) {
+  int r = 2;
+  for (int R = 2; R <= 32; ++R) if ((size_t)KP * prof_stride_rows(R) * 128 <= bytes) r = R;
+  return r;
+}
+
 // Rows per lane of the strip geometry (L = 32) for a batch whose longest sequence has m_max rows.  With few long
 // pairs (the long-pair config) the strips of a pair run concurrently, one warp each, so thin strips are preferred — as
 // thin as the HBM budget for the strip boundary rows allows — to put a warp on every SM sub-partition; *few_long tells
 // the caller that this mode applies.
 int strip_rows(const swb_ctx* ctx, uint32_t m_max, uint32_t n_max, size_t npairs_est, bool profile, bool* few_long) {
-  const int r_hard = profile ? std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128)))) : 32;
-  const int r_pref = profile ? std::max(2, std::min(r_hard, (int)(14336 / ((size_t)ctx->KP * 128)))) : 32;
+  const int r_hard = profile ? max_rows_for_profile(ctx->KP, 200 * 1024) : 32;
+  const int r_pref = profile ? std::min(r_hard, max_rows_for_profile(ctx->KP, 14336)) : 32;
   int r_strip = kRSet[0];
   const int cap = profile ? r_pref : 32;
   for (int i = 0; i < kNumR; ++i) if (kRSet[i] <= cap) r_strip = kRSet[i];
@@ -322,11 +332,12 @@ int strip_rows(const swb_ctx* ctx, uint32_t m_max, uint32_t n_max, size_t npairs
   if (npairs_est < 148 * 8 && (int)m_max > 32 * r_strip) {
     if (few_long) *few_long = true;
     // boundary rows: up to three quarters of the free HBM (at least 32 GiB), SWB_BND_BUDGET_MB overrides.  10 kbp x 51 Mbp:
-    // 4 rows per lane need 127 GB (79 strips per pair, 632 warps), 8 rows 64 GB (320 warps)
+    // 4 rows per lane need 127 GB (79 strips per pair, 632 units), 5 rows 101 GB (504 units), 8 rows 64 GB (320 units)
     size_t budget_mb = 32768;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget_mb = std::max<size_t>(budget_mb, (free_b + ctx->d_bnd.cap) / 4 * 3 / 1048576);
     if (const char* e = getenv("SWB_BND_BUDGET_MB")) budget_mb = (size_t)std::max(64L, atol(e));
+    // ... until a round of tasks holds at least one unit per SM sub-partition (the persistent warps of score_units_kernel)
     for (int i = kNumR - 1; i >= 0; --i) {
       const int R = kRSet[i];
       if (R > r_strip || R < 4) continue;
@@ -334,7 +345,7 @@ int strip_rows(const swb_ctx* ctx, uint32_t m_max, uint32_t n_max, size_t npairs
       const double bytes = (strips - 1) * ((double)n_max + 1) * 4.0 * (double)npairs_est;
       if (bytes > (double)budget_mb * 1048576.0) break;
       r_strip = R;
-      if (strips * (double)npairs_est >= 148.0 * 4.0) break;      // one warp per SM sub-partition is enough
+      if (strips * (double)npairs_est >= 4.0 * ctx->sm_count) break;
     }
   }
   if (const char* e = getenv("SWB_STRIP_R")) {
@@ -352,8 +363,8 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
   const bool profile = use_profile(ctx, false);
   // rows per lane: up to 32 registers; with the profile select prefer a per-warp profile <= 14 KB (16 warps / SM)
   // and never exceed what one warp's profile can hold in shared memory
-  const int r_hard = profile ? std::max(2, std::min(32, (int)(200 * 1024 / ((size_t)ctx->KP * 128)))) : 32;
-  const int r_pref = profile ? std::max(2, std::min(r_hard, (int)(14336 / ((size_t)ctx->KP * 128)))) : 32;
+  const int r_hard = profile ? max_rows_for_profile(ctx->KP, 200 * 1024) : 32;
+  const int r_pref = profile ? std::min(r_hard, max_rows_for_profile(ctx->KP, 14336)) : 32;
   // geometry per distinct m
   std::map<uint32_t, size_t> count_by_m;
   for (auto& s : seeds) count_by_m[s.m]++;
@@ -538,7 +549,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     int warps_per_cta = 4;
     size_t smem = 0;
     if (profile) {
-      const size_t per_warp = (size_t)ctx->KP * R * 32 * 4;
+      const size_t per_warp = (size_t)ctx->KP * prof_stride_rows(R) * 32 * 4;
       while (warps_per_cta > 1 && per_warp * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
       smem = per_warp * warps_per_cta;
       if (const char* e = getenv("SWB_EXTRA_SMEM")) smem += (size_t)atol(e);   // occupancy experiments
@@ -557,17 +568,32 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
         for (size_t pi = 0; pi < lc.pairs.size(); ++pi)
           for (uint32_t st = 0; st < lc.pairs[pi].nstrips; ++st) units.push_back(make_uint2((unsigned)pi, st));
         CUDA_TRY(ctx->d_units.ensure(units.size() * sizeof(uint2)));
-        CUDA_TRY(ctx->d_progress.ensure((units.size() + 2) * 4));
+        CUDA_TRY(ctx->d_progress.ensure((2 * units.size() + 2) * 4));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_units.p, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(ctx->d_progress.p, 0, (units.size() + 2) * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_progress.p, 0, (2 * units.size() + 2) * 4, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));      // `units` is a host temporary
         pp.units = ctx->d_units.as<uint2>(); pp.nunits = (int)units.size();
         pp.progress = ctx->d_progress.as<uint32_t>();
         pp.abort_flag = ctx->d_progress.as<uint32_t>() + units.size();
         pp.ticket = ctx->d_progress.as<uint32_t>() + units.size() + 1;
-        warps = units.size();
-        warps_per_cta = 1;                                   // spread the units over all SMs
-        if (profile) smem = (size_t)ctx->KP * R * 32 * 4;
+        pp.blocks_done = ctx->d_progress.as<uint32_t>() + units.size() + 2;
+        // a task = one unit x enough checkpoint blocks for 256 steps (64 .. 128 when the reference is so short that the
+        // 2 * strips rounds it takes to fill the pipeline would show); tickets run round-major, task block = round - 2 * strip
+        uint32_t nblk_max = 1;
+        for (auto& pd : lc.pairs) nblk_max = std::max(nblk_max, pd.nblk);
+        int task_steps = 256;
+        while (task_steps > 64 && (uint64_t)nblk_max * ctx->B / task_steps < 16ull * lc.max_strips) task_steps >>= 1;
+        pp.task_blocks = std::max(1, task_steps / ctx->B);
+        if (const char* e = getenv("SWB_TASK_BLOCKS")) pp.task_blocks = std::max(1, atoi(e));
+        uint64_t rounds = 0;
+        for (auto& pd : lc.pairs) rounds = std::max<uint64_t>(rounds, 2ull * (pd.nstrips - 1) + (pd.nblk + pp.task_blocks - 1) / pp.task_blocks);
+        if (rounds * units.size() >= 0xffffffffull) return fail(ctx, SWB_ERR_UNSUPPORTED, "pipelined strips: too many tasks");
+        pp.ntickets = (uint32_t)(rounds * units.size());
+        // persistent warps: one per SM sub-partition, never more than there are units in a round
+        warps = std::min<size_t>(units.size(), (size_t)4 * (size_t)ctx->sm_count);
+        if (const char* e = getenv("SWB_UNIT_WARPS")) warps = std::max<size_t>(1, std::min<size_t>(units.size(), (size_t)atol(e)));
+        warps_per_cta = 1;                                   // spread the warps over all SMs
+        if (profile) smem = (size_t)ctx->KP * prof_stride_rows(R) * 32 * 4;
       }
       const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
       CUDA_TRY(launch_score(R, ctx->C, am, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, pp));
@@ -581,7 +607,6 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
         if (aborted) return fail(ctx, SWB_ERR_CUDA, "pipelined strips: a strip timed out waiting for its producer");
         pp.units = nullptr; pp.nunits = 0;
         warps_per_cta = 4;
-        if (profile) { const size_t per_warp = (size_t)ctx->KP * R * 32 * 4; while (warps_per_cta > 1 && per_warp * warps_per_cta > 200 * 1024) warps_per_cta >>= 1; smem = per_warp * warps_per_cta; }
       }
     }
     if (!trace && !select_pieces) continue;
@@ -905,6 +930,7 @@ int swb_create(int device, swb_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
   swb_ctx* ctx = new swb_ctx();
   ctx->device = device;
+  if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0) ctx->sm_count = 148;
   memset(ctx->code_of, 0xFF, sizeof ctx->code_of);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SWB_ERR_CUDA; }
   for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SWB_ERR_CUDA; }
