@@ -811,6 +811,7 @@ struct TraceParams {
   const TaskDesc* tasks;      // indexed through task_list when non-null
   const uint32_t* task_list;
   int ntasks;
+  uint32_t* next_task;        // zeroed by the host before the launch: first task nobody has taken yet
   int mode;                   // MODE_SAT_U8: skewed raw-order tie-break; MODE_EXACT: column-major
   int max_pos;                // largest positive substitution score: a cell of score V needs row >= ceil(V / max_pos)
   uint32_t* scratch;          // per warp: nlc local checkpoints (lane states), word (slot * state_words + w) * 32 + lane
@@ -878,7 +879,6 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
   const int grp_in_warp = lane >> p.logL;
   const int groups_per_warp = 32 >> p.logL;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int wmask = tp.Wc - 1;
   const int G = p.sc.G;
   const int S = L * R;                 // rows per strip
@@ -889,7 +889,14 @@ __device__ __forceinline__ void trace_body(const TraceParams& tp, uint32_t* smem
   WF wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
 
-  for (int base = gwarp * groups_per_warp; base < tp.ntasks; base += nwarps * groups_per_warp) {   // warp-uniform
+  // A warp takes the next 32/L tasks from a counter when it has finished its last ones: alignments differ in length
+  // (sessions, walk) and not every thread block of the launch is resident from the start, so a fixed stride over the
+  // tasks left the SMs idle for 13-22 % of the kernel at its end (ncu: sm__cycles_elapsed.max vs smsp__cycles_active.avg).
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = (int)atomicAdd(tp.next_task, (uint32_t)groups_per_warp);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= tp.ntasks) break;                                 // warp-uniform
     const int ti = base + grp_in_warp;
     bool active = ti < tp.ntasks;
     const TaskDesc td = tp.tasks[tp.task_list ? tp.task_list[active ? ti : base] : (active ? ti : base)];

@@ -106,7 +106,7 @@ struct swb_ctx {
   bool force_l32 = false;           // swb_matrix: always the 32-lane geometry (one pair per warp)
   int C = 1;                        // columns per wavefront step (2 = more ILP per warp; measured slower on B200, kept selectable)
   std::vector<LaunchClass> classes;
-  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress;
+  DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress, d_next_task;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
   DevBuf d_check;                     // SWB_CHECKED builds: one word, the highest failing bounds-check site
   // query-stationary mode (sw_qs.cuh): database search against a short reference, computed transposed
@@ -660,6 +660,9 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.cons_cap = (uint32_t)ctx->cons_stride;
     tp.want_consensus = (ctx->flags & SWB_FLAG_CONSENSUS) ? 1 : 0;
     if (!tp.want_consensus) tp.cons_cap = 0x7FFFFFFFu;
+    CUDA_TRY(ctx->d_next_task.ensure(256));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_next_task.p, 0, 4, ctx->stream));
+    tp.next_task = ctx->d_next_task.as<uint32_t>();
     DevBuf d_cnt;
     tp.counters = nullptr;
     tp.dbg_flags = getenv("SWB_DEBUG_FLAGS") ? atoi(getenv("SWB_DEBUG_FLAGS")) : 0;
@@ -881,6 +884,9 @@ int run_qs(swb_ctx* ctx) {
     tp.cons_cap = (uint32_t)ctx->cons_stride;
     tp.want_consensus = (ctx->flags & SWB_FLAG_CONSENSUS) ? 1 : 0;
     if (!tp.want_consensus) tp.cons_cap = 0x7FFFFFFFu;
+    CUDA_TRY(ctx->d_next_task.ensure(256));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_next_task.p, 0, 4, ctx->stream));
+    tp.next_task = ctx->d_next_task.as<uint32_t>();
     DevBuf d_cnt;
     tp.counters = nullptr;
     tp.dbg_flags = 0;
@@ -942,7 +948,7 @@ void swb_destroy(swb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   free_classes(ctx->classes);
-  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd, &ctx->d_units, &ctx->d_progress,
+  for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd, &ctx->d_units, &ctx->d_progress, &ctx->d_next_task,
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
                     &ctx->d_len, &ctx->d_flags, &ctx->d_xcode, &ctx->d_qs_table, &ctx->d_check}) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -1074,6 +1080,10 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
   if ((flags & SWB_FLAG_CONSENSUS) && cons_stride == 0) return fail(ctx, SWB_ERR_ARG, "cons_stride must be > 0 when consensus is requested");
   CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->staged = false;
+  // SWB_DEBUG_STAGE=1: host wall time of the stage's parts on stderr (where end-to-end time goes besides the kernels)
+  const bool dbg_stage = getenv("SWB_DEBUG_STAGE") != nullptr;
+  double ts_prev = dbg_stage ? DebugTimer::now() : 0.0;
+  auto lap = [&](const char* what) { if (dbg_stage) { const double t = DebugTimer::now(); fprintf(stderr, "[swb200 stage] %-18s %8.3f ms\n", what, t - ts_prev); ts_prev = t; } };
   const size_t N = ctx->y.size();
   const size_t blob = offsets[n_seqs] - offsets[0];
   if (blob > 0xFFFF0000ull) return fail(ctx, SWB_ERR_UNSUPPORTED, "sequence blob larger than 4 GiB (split the batch)");
@@ -1166,15 +1176,20 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     if (const char* e = getenv("SWB_FORCE_B")) B = std::max(32, std::min(65536, 1 << ilog2(atoi(e))));
     ctx->B = B; ctx->logB = ilog2(B);
   }
+  lap("seeds + geometry");
   int rc = upload_profile_table(ctx);
   if (rc) return rc;
   free_classes(ctx->classes);
+  lap("free classes");
   rc = build_classes(ctx, seeds, pieces, &ctx->classes);
   if (rc) return rc;
+  lap("build classes");
   CUDA_TRY(ctx->d_reads.ensure(blob + 64));
   CUDA_TRY(cudaMemcpyAsync(ctx->d_reads.p, seqs + offsets[0], blob, cudaMemcpyHostToDevice, ctx->stream));
+  lap("H2D sequences");
   rc = upload_classes(ctx, ctx->classes);
   if (rc) return rc;
+  lap("upload classes");
   // outputs
   CUDA_TRY(ctx->d_score.ensure(n_seqs * 4));
   CUDA_TRY(ctx->d_pos.ensure(n_seqs * 4));
@@ -1186,6 +1201,7 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
     CUDA_TRY(ctx->d_cy.ensure(n_seqs * cons_stride));
   }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  lap("outputs + sync");
   ctx->stats = swb_stats{};
   ctx->stats.cells_reference = cells_ref;
   ctx->staged = true;
