@@ -108,6 +108,7 @@ struct swb_ctx {
   std::vector<LaunchClass> classes;
   DevBuf d_reads, d_qpairs, d_blkmax, d_ckpt, d_bnd, d_scratch, d_taskmax, d_winner, d_units, d_progress, d_next_task;
   DevBuf d_score, d_pos, d_end, d_cx, d_cy, d_len, d_flags;
+  std::vector<DevBuf> desc_pool;      // descriptor buffers of finished launch classes, reused by the next stage
   DevBuf d_check;                     // SWB_CHECKED builds: one word, the highest failing bounds-check site
   // query-stationary mode (sw_qs.cuh): database search against a short reference, computed transposed
   bool qs = false;
@@ -487,8 +488,24 @@ int build_classes(swb_ctx* ctx, const std::vector<TaskSeed>& seeds, int pieces, 
   return SWB_OK;
 }
 
+// The descriptor buffers of the classes come from a pool in the context and go back to it: cudaFree / cudaMalloc per staged
+// batch cost 1 .. 500 ms on a GPU that holds gigabytes of work buffers (measured with SWB_DEBUG_STAGE: "free classes").
+DevBuf take_desc_buf(swb_ctx* ctx, size_t bytes) {
+  int best = -1;
+  for (size_t i = 0; i < ctx->desc_pool.size(); ++i) {
+    const DevBuf& b = ctx->desc_pool[i];
+    if (b.cap >= bytes && (best < 0 || b.cap < ctx->desc_pool[best].cap)) best = (int)i;
+  }
+  if (best < 0 && !ctx->desc_pool.empty()) best = (int)ctx->desc_pool.size() - 1;   // too small: ensure() regrows it
+  DevBuf b;
+  if (best >= 0) { b = ctx->desc_pool[best]; ctx->desc_pool.erase(ctx->desc_pool.begin() + best); }
+  return b;
+}
+
 int upload_classes(swb_ctx* ctx, std::vector<LaunchClass>& classes) {
   for (auto& lc : classes) {
+    if (!lc.d_pairs.p) lc.d_pairs = take_desc_buf(ctx, lc.pairs.size() * sizeof(PairDesc));
+    if (!lc.d_tasks.p) lc.d_tasks = take_desc_buf(ctx, lc.tasks.size() * sizeof(TaskDesc));
     CUDA_TRY(lc.d_pairs.ensure(lc.pairs.size() * sizeof(PairDesc)));
     CUDA_TRY(lc.d_tasks.ensure(lc.tasks.size() * sizeof(TaskDesc)));
     CUDA_TRY(cudaMemcpyAsync(lc.d_pairs.p, lc.pairs.data(), lc.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
@@ -497,9 +514,14 @@ int upload_classes(swb_ctx* ctx, std::vector<LaunchClass>& classes) {
   return SWB_OK;
 }
 
-void free_classes(std::vector<LaunchClass>& classes) {
-  for (auto& lc : classes) { lc.d_pairs.release(); lc.d_tasks.release(); }
+void free_classes(swb_ctx* ctx, std::vector<LaunchClass>& classes) {
+  for (auto& lc : classes) {
+    if (lc.d_pairs.p) ctx->desc_pool.push_back(lc.d_pairs);
+    if (lc.d_tasks.p) ctx->desc_pool.push_back(lc.d_tasks);
+    lc.d_pairs = DevBuf{}; lc.d_tasks = DevBuf{};
+  }
   classes.clear();
+  while (ctx->desc_pool.size() > 64) { ctx->desc_pool.back().release(); ctx->desc_pool.pop_back(); }
 }
 
 // Run pass 1 (+ piece selection) + pass 2 for every class.  `force_default`: plocalaligner.cpp:135 re-alignment.
@@ -637,13 +659,19 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     tp.max_pos = force_default ? 3 : std::max(1, hs.max_pos);
     const TraceGeom tg = trace_geometry(L, R, ctx->C, sat, wide);
     tp.Wc = tg.Wc; tp.logWc = tg.logWc; tp.NB = tg.NB; tp.nlc = tg.nlc;
-    const size_t prof_words_warp = profile ? (size_t)ctx->KP * R * 32 : 0;
+    // Pass 2 is latency-bound, not ALU-bound: with match/mismatch scoring it gives up the per-warp profile (10 KB of shared
+    // memory at 16 rows x 5 symbols, rebuilt per task) for two more ALU instructions per cell pair and a fourth resident
+    // block per SM (measured: pass 2 of C1x64 1.90 -> 1.69 ms, C3 24.5 -> 20.4 ms; SWB_TRACE_SELECT=profile is the old way).
+    bool tprofile = profile;
+    if (profile && (hs.match_shaped || force_default))
+      tprofile = getenv("SWB_TRACE_SELECT") && !strcmp(getenv("SWB_TRACE_SELECT"), "profile");
+    const size_t prof_words_warp = tprofile ? (size_t)ctx->KP * R * 32 : 0;
     warps_per_cta = 4;
     while (warps_per_cta > 1 && (prof_words_warp + tg.ring_words) * 4 * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
     tp.ring_off = (int)(prof_words_warp * warps_per_cta);
     smem = (prof_words_warp + tg.ring_words) * 4 * warps_per_cta;
     if (smem > 220 * 1024) return fail(ctx, SWB_ERR_UNSUPPORTED, "pass-2 ring does not fit shared memory (lower SWB_TRACE_WC / SWB_TRACE_NB)");
-    const size_t max_groups = (size_t)148 * 16 * groups_per_warp;
+    const size_t max_groups = (size_t)ctx->sm_count * 24 * groups_per_warp;   // up to 6 blocks per SM; the warps take tasks from a counter, surplus blocks exit at once
     size_t groups = std::min<size_t>((size_t)ntrace, max_groups);
     size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
@@ -669,7 +697,7 @@ int run_classes(swb_ctx* ctx, LaunchClass* classes, size_t nclasses, bool force_
     if (dbg.on) { CUDA_TRY(d_cnt.ensure(128)); CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 128, ctx->stream)); tp.counters = d_cnt.as<unsigned long long>(); }
     while (ctx->ev_pool.size() < ctx->ev_used + 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
     CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
-    CUDA_TRY(launch_trace(R, ctx->C, am, profile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
+    CUDA_TRY(launch_trace(R, ctx->C, am, tprofile, dim3(grid), dim3(32 * warps_per_cta), smem, ctx->stream, tp));
     CUDA_TRY(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
     ctx->ev_used += 2;
     ctx->stats.kernel_launches++;
@@ -773,7 +801,7 @@ int stage_qs(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, size_t n_s
     if (worst * 4 <= budget_mb * 1048576 || B >= 65536) break;
   }
   ctx->B = B; ctx->logB = ilog2(B);
-  free_classes(ctx->classes);
+  free_classes(ctx, ctx->classes);
   for (size_t o = 0; o < n_seqs; o += chunk_tasks) {
     ctx->classes.emplace_back();
     LaunchClass& lc = ctx->classes.back();
@@ -867,7 +895,7 @@ int run_qs(swb_ctx* ctx) {
     while (warps_per_cta > 1 && smem_trace + tg.ring_words * 4 * warps_per_cta > 200 * 1024) warps_per_cta >>= 1;
     const size_t smem_trace_total = smem_trace + tg.ring_words * 4 * warps_per_cta;
     if (smem_trace_total > 220 * 1024) return fail(ctx, SWB_ERR_UNSUPPORTED, "pass-2 ring does not fit shared memory (lower SWB_TRACE_WC / SWB_TRACE_NB)");
-    const size_t max_groups = (size_t)148 * 16 * groups_per_warp;
+    const size_t max_groups = (size_t)ctx->sm_count * 24 * groups_per_warp;   // up to 6 blocks per SM; the warps take tasks from a counter, surplus blocks exit at once
     const size_t groups = std::min<size_t>(lc.tasks.size(), max_groups);
     const size_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
     const unsigned grid = (unsigned)((warps + warps_per_cta - 1) / warps_per_cta);
@@ -947,7 +975,8 @@ int swb_create(int device, swb_ctx** out) {
 void swb_destroy(swb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  free_classes(ctx->classes);
+  free_classes(ctx, ctx->classes);
+  for (auto& b : ctx->desc_pool) b.release();
   for (DevBuf* b : {&ctx->d_ref_raw, &ctx->d_ref_code, &ctx->d_table, &ctx->d_reads, &ctx->d_qpairs, &ctx->d_blkmax, &ctx->d_ckpt, &ctx->d_bnd, &ctx->d_units, &ctx->d_progress, &ctx->d_next_task,
                     &ctx->d_scratch, &ctx->d_taskmax, &ctx->d_winner, &ctx->d_score, &ctx->d_pos, &ctx->d_end, &ctx->d_cx, &ctx->d_cy,
                     &ctx->d_len, &ctx->d_flags, &ctx->d_xcode, &ctx->d_qs_table, &ctx->d_check}) b->release();
@@ -1179,7 +1208,7 @@ int swb_batch_stage(swb_ctx* ctx, const char* seqs, const uint64_t* offsets, siz
   lap("seeds + geometry");
   int rc = upload_profile_table(ctx);
   if (rc) return rc;
-  free_classes(ctx->classes);
+  free_classes(ctx, ctx->classes);
   lap("free classes");
   rc = build_classes(ctx, seeds, pieces, &ctx->classes);
   if (rc) return rc;
@@ -1251,7 +1280,7 @@ int swb_batch_run(swb_ctx* ctx, float* device_us) {
     if (!rc) rc = upload_classes(ctx, second);
     if (!rc) rc = run_classes(ctx, second.data(), second.size(), true, false, true);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    free_classes(second);
+    free_classes(ctx, second);
     if (rc) return rc;
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SWB_ERR_CUDA; }
   }
