@@ -90,8 +90,16 @@ def issue_fraction(counts, st, sat, p_int):
     if e is None or st["pass1_us"] <= 0:
         return None
     pairs_per_s = st["cells_executed"] / 2.0 / (st["pass1_us"] * 1e-6)
-    return {"frac": e["alu_inst_per_cell_pair"] * pairs_per_s / (p_int * 1e12), "alu_inst_per_cell_pair": e["alu_inst_per_cell_pair"],
-            "inst_per_cell_pair": e["inst_per_cell_pair"], "kernel": key}
+    # kernels whose SASS loop holds paths not taken in the steady state carry EXECUTED counts from an ncu capture
+    # (tools/sass_counts.py EXECUTED); the static count is kept beside them
+    ex = e.get("executed")
+    alu = ex["alu_inst_per_cell_pair"] if ex else e["alu_inst_per_cell_pair"]
+    out = {"frac": alu * pairs_per_s / (p_int * 1e12), "alu_inst_per_cell_pair": alu,
+           "inst_per_cell_pair": ex["inst_per_cell_pair"] if ex else e["inst_per_cell_pair"], "kernel": key,
+           "counts_from": ("from_profile: " + ex["source"]) if ex else "SASS of the built object (tools/sass_counts.py)"}
+    if ex:
+        out["alu_inst_per_cell_pair_static_sass"] = e["alu_inst_per_cell_pair"]
+    return out
 
 
 class ClockSampler:
@@ -294,7 +302,7 @@ def entry(st, us, counts, sat, p_int, extra=None):
                       "block_steps": st["block_steps"], "pass1_kernel": ["score_kernel", "score_units_kernel", "qs_score_kernel"][st["kernel_kind"]]}}
     fr = issue_fraction(counts, st, sat, p_int)
     if fr:
-        e["roofline"] = {"bound": "alu", "frac": fr["frac"], "alu_inst_per_cell_pair": fr["alu_inst_per_cell_pair"], "kernel": fr["kernel"], "peak_tera_lane_ops": p_int,
+        e["roofline"] = {"bound": "alu", "frac": fr["frac"], "alu_inst_per_cell_pair": fr["alu_inst_per_cell_pair"], "counts_from": fr["counts_from"], "kernel": fr["kernel"], "peak_tera_lane_ops": p_int,
                          "frac_contract_9ops": st["cells_reference"] / (st["pass1_us"] * 1e-6) * OPS_PER_CELL["SAT_U8" if sat else "EXACT"] / (p_int * 1e12)}
     if extra:
         e.update(extra)

@@ -1,14 +1,26 @@
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/r02ab_pytest.log
-( timeout 200 python tools/fuzz_parity.py 200 31337 2>&1 | tail -5 ) > gpurun_out/r02ab_fuzz.log
-timeout 900 python bench.py > gpurun_out/r02ab_bench_1gpu.json 2> gpurun_out/r02ab_bench_1gpu.err
-timeout 300 python bench.py --impl reference > gpurun_out/r02ab_bench_reference_arm.json 2> gpurun_out/r02ab_bench_reference_arm.err
-SWB_DEBUG_STAGE=1 timeout 300 python bench.py --steps 3 --no-configs --no-cpu-baseline > gpurun_out/r02ab_bench_stage.json 2> gpurun_out/r02ab_bench_stage.err
-cat gpurun_out/r02ab_pytest.log gpurun_out/r02ab_fuzz.log; grep "free classes\|upload classes" gpurun_out/r02ab_bench_stage.err | sort -k5 -n | tail -4
-python - <<'P'
-import json
-for f in ['gpurun_out/r02ab_bench_1gpu.json','gpurun_out/r02ab_bench_stage.json']:
-  for l in open(f):
-    if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['e2e']['value'], d['e2e']['parts'])
-P
+export RUN_REPS=1
+T0=$(date +%s)
+M=sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__cycles_active.avg,sm__cycles_elapsed.max,smsp__issue_active.avg.pct_of_peak_sustained_active
+SEC="--section SpeedOfLight --section SchedulerStats --section WarpStateStats --section LaunchStats --section Occupancy"
+full() { # name, kernel regex, count, which, args...
+  name=$1; k=$2; c=$3; which=$4; shift 4
+  timeout 240 ncu --set full --clock-control none -f -k regex:$k -c $c -o gpurun_out/r02ad_$name python tools/run_config.py "$@" > gpurun_out/r02ad_ncu_$name.log 2>&1
+  echo "$name rc=$? t=$(( $(date +%s) - T0 ))"
+  python tools/ncu_summary.py gpurun_out/r02ad_$name.ncu-rep $which > gpurun_out/r02ad_${name}_summary.txt 2>&1
+  rm -f gpurun_out/r02ad_$name.ncu-rep
+}
+full trace_c1x64 '^trace_kernel' 1 trace_kernel c1x64
+full qs_c4 'qs_' 2 qs_ c4 100000
+full units_c5_2M 'score_units_kernel' 1 score_units c5 2000000
+timeout 300 ncu --replay-mode application --clock-control none -f -k regex:score_units_kernel -c 1 $SEC --metrics $M \
+  -o gpurun_out/r02ad_units_c5_51M python tools/run_config.py c5 51000000 > gpurun_out/r02ad_ncu_units_c5_51M.log 2>&1
+echo "units 51M rc=$? t=$(( $(date +%s) - T0 ))"
+python tools/ncu_summary.py gpurun_out/r02ad_units_c5_51M.ncu-rep score_units > gpurun_out/r02ad_units_c5_51M_summary.txt 2>&1; rm -f gpurun_out/r02ad_units_c5_51M.ncu-rep
+timeout 240 ncu --clock-control none -f -k 'regex:^score_kernel' -c 1 $SEC --metrics $M,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum \
+  -o gpurun_out/r02ad_score_c3 python tools/run_config.py c3 75776 > gpurun_out/r02ad_ncu_score_c3.log 2>&1
+echo "score c3 rc=$? t=$(( $(date +%s) - T0 ))"
+python tools/ncu_summary.py gpurun_out/r02ad_score_c3.ncu-rep score_kernel > gpurun_out/r02ad_score_c3_summary.txt 2>&1; rm -f gpurun_out/r02ad_score_c3.ncu-rep
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02ad_launches.csv python bench.py --steps 2 --warmup 3 --no-configs --no-cpu-baseline > gpurun_out/r02ad_ncu_launches.log 2>&1
+echo "launch list rc=$? t=$(( $(date +%s) - T0 ))"
+rm -f gpurun_out/*.ncu-rep; du -sh gpurun_out; head -12 gpurun_out/r02ad_units_c5_51M_summary.txt

@@ -44,6 +44,19 @@ KERNELS = {
 }
 
 
+# EXECUTED instructions per cell pair, from ncu counters, for kernels whose loop body holds paths that are not taken in the
+# steady state (score_units_kernel: progress polling, NANOSLEEP, writer-lane and chunk hand-off code) — there the static
+# count overstates the work: 8.9 instructions per cell pair in the SASS loop, 7.3 executed.
+#   profiles/score_units_kernel_r02_c5_ncu.txt (2), 16 x 10 kbp x 51 Mbp EXACT, one launch: smsp__inst_executed.sum = 941 937 707 768,
+#   ALU pipe 36.397 % of 0.5 warp-instructions/clk x 3 963 930 802 active cycles x 592 sub-partitions = 4.2706e11 instructions,
+#   cell pairs per lane = 79 strips x 128 rows x 51 003 392 columns x 8 pairs / 32 lanes = 1.2894e11.
+# The SAT_U8 variant has the same static ALU count (334 per trip) and was not captured: the EXACT figures are used for it.
+EXECUTED = {
+    "score_units_kernel<R=4,C=8,": dict(alu_inst_per_cell_pair=3.3121, inst_per_cell_pair=7.3054,
+                                        source="ncu, profiles/score_units_kernel_r02_c5_ncu.txt (2): 10 kbp x 51 Mbp, EXACT"),
+}
+
+
 def registers(obj, kernel):
     out = subprocess.run(["cuobjdump", "--dump-resource-usage", os.path.join(OBJ, obj)], capture_output=True, text=True, check=True).stdout
     m = re.search(re.escape(kernel) + r":\s*\n\s*REG:(\d+)", out)
@@ -86,6 +99,10 @@ def loop_mix(obj, kernel, cell_pairs):
 def main():
     doc = {"how": "tools/sass_counts.py: smallest backward-branch loop of each kernel holding >= 2 VIADDMNMX per cell pair (cuobjdump -sass of parallel-genomeseq_b200/build/*.o)",
            "kernels": {k: loop_mix(*v) for k, v in KERNELS.items()}}
+    for k, v in doc["kernels"].items():
+        for pat, ex in EXECUTED.items():
+            if pat in k:
+                v["executed"] = ex
     if "--check" in sys.argv:
         with open(OUT) as f:
             old = json.load(f)
