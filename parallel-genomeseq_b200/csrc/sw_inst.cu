@@ -83,7 +83,8 @@ cudaError_t SWB_CAT(swb_launch_trace_r, SWB_R)(int C, int am, bool profile, dim3
 }
 
 // query-stationary kernels (sw_qs.cuh): one column per step, profile select
-cudaError_t SWB_CAT(swb_launch_qs_score_r, SWB_R)(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsParams& p) {
+cudaError_t SWB_CAT(swb_launch_qs_score_r, SWB_R)(bool sat, bool p16, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsParams& p) {
+  if (p16) return sat ? go(qs_score_kernel<SWB_R, true, true>, grid, block, smem, st, p) : go(qs_score_kernel<SWB_R, false, true>, grid, block, smem, st, p);
   return sat ? go(qs_score_kernel<SWB_R, true>, grid, block, smem, st, p) : go(qs_score_kernel<SWB_R, false>, grid, block, smem, st, p);
 }
 cudaError_t SWB_CAT(swb_launch_qs_trace_r, SWB_R)(bool sat, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const QsTraceParams& p) {

@@ -15,6 +15,7 @@
 // by (query byte | 256 = padding row, batch code | KP-1 = padding column).
 #pragma once
 #include "sw_core.cuh"
+#include <type_traits>
 
 namespace swb {
 
@@ -24,7 +25,8 @@ struct QsTraceParams { TraceParams tp; int m; };
 // prof[(code*R + k)*32 + lane] = score of row (lane & (L-1))*R + k against batch code `code`, as PT.
 // PT = uint32_t: pack(s, s), one bank per lane — the score pass (measured 1.4x faster than the 16-bit form there).
 // PT = uint16_t: half the shared memory (both halves of a register sit in the same row, so one 16-bit entry
-// serves either) — pass 2, where more resident warps hide the latency of the replay and of the walk.
+// serves either) — pass 2, where more resident warps hide the latency of the replay and of the walk; stored in the
+// PAIRED layout below (qs_build_profile_paired), this builder then only serves the 32-bit form.
 template <int R, class PT>
 __device__ __forceinline__ void qs_build_profile(uint32_t* prof32, const PassParams& p, int m) {
   PT* prof = reinterpret_cast<PT*>(prof32);
@@ -36,6 +38,33 @@ __device__ __forceinline__ void qs_build_profile(uint32_t* prof32, const PassPar
     const int a = row < m ? (int)p.reads_raw[row] : 256;
     const uint32_t v = (uint32_t)(uint16_t)p.table[a * p.KP + code];
     prof[idx] = (PT)(sizeof(PT) == 4 ? v * 0x00010001u : v);
+  }
+  __syncthreads();
+}
+
+// Pass-2 profile (PT = uint16_t), PAIRED layout: word (code*RH + k/2)*32 + lane, RH = (R+1)/2, holds the 16-bit scores of the
+// lane's rows k (low half) and k+1 (high half, k even) against batch code `code`.  Bank = lane whatever the codes of the
+// lanes are (every lane of the skewed wavefront is on a different column), and one LDS serves two rows: 20 loads per step
+// at 19 rows instead of 38.  (The plain 16-bit layout [(code*R + k)*32 + lane] put lanes 2i and 2i+1 into one bank with
+// different words whenever their codes differed in parity: ncu showed 111 M conflict wavefronts in 245 M.)
+template <int R>
+__device__ __forceinline__ void qs_build_profile_paired(uint32_t* prof, const PassParams& p, int m) {
+  constexpr int RH = (R + 1) / 2;
+  const int total = p.KP * RH * 32;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int lane = idx & 31, kc = idx >> 5;
+    const int code = kc / RH, k2 = kc - code * RH;
+    uint32_t v = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * k2 + h;
+      if (k < R) {
+        const int row = (lane & (p.L - 1)) * R + k;
+        const int a = row < m ? (int)p.reads_raw[row] : 256;
+        v |= (uint32_t)(uint16_t)p.table[a * p.KP + code] << (16 * h);
+      }
+    }
+    prof[idx] = v;
   }
   __syncthreads();
 }
@@ -52,6 +81,19 @@ struct DualProfileSelect {
   }
 };
 
+template <int R>
+struct DualProfileSelect<R, uint16_t> {
+  static constexpr int RH = (R + 1) / 2;
+  const uint32_t* prof;   // shared memory, already offset by lane (paired layout, qs_build_profile_paired)
+  const uint32_t* colA;
+  const uint32_t* colB;
+  __device__ __forceinline__ void set_column(uint32_t ca, uint32_t cb) { colA = prof + ca * (RH * 32); colB = prof + cb * (RH * 32); }
+  // rows k and k+1 (k even) share a word: low halves of A and B for the even row, high halves for the odd one
+  __device__ __forceinline__ uint32_t operator()(int k, int) const {
+    return __byte_perm(colA[(k >> 1) * 32], colB[(k >> 1) * 32], (k & 1) ? 0x7632 : 0x5410);
+  }
+};
+
 template <int R, bool SAT, class PT>
 struct QsWavefront {
   static constexpr int C = 1;
@@ -65,7 +107,7 @@ struct QsWavefront {
 
   __device__ __forceinline__ size_t blk_index(const PairDesc&, int b) const { return (size_t)b; }
   __device__ __forceinline__ size_t ck_index(const PairDesc&, int b) const { return (size_t)b * state_words<R, 1, SAT>() * L; }
-  __device__ __forceinline__ void prepare(const PairDesc&, int, uint32_t* prof_cta) { dsel.prof = reinterpret_cast<const PT*>(prof_cta) + lane; }
+  __device__ __forceinline__ void prepare(const PairDesc&, int, uint32_t* prof_cta) { dsel.prof = reinterpret_cast<decltype(dsel.prof)>(prof_cta) + lane; }
   const uint32_t* restore_from = nullptr;   // local checkpoint of pass 2 (see Wavefront::restore_from)
   __device__ __forceinline__ void restore(const PairDesc& pd, int t0) {
     if (t0 == 0) init_state<R, 1>(st, p.sc);
@@ -137,11 +179,14 @@ struct QsWavefront {
 };
 
 // Score pass: one group of L lanes per pair of database sequences, 32/L pairs per warp.
-template <int R, bool SAT>
+// P16: the paired 16-bit profile of pass 2 (half the loads and half the shared memory) instead of the 32-bit one; SWB_QS_PROF16=1.
+template <int R, bool SAT, bool P16 = false>
 __global__ void __launch_bounds__(128) qs_score_kernel(const QsParams qp) {
   extern __shared__ uint32_t smem_prof[];
   const PassParams& p = qp.pp;
-  qs_build_profile<R, uint32_t>(smem_prof, p, qp.m);
+  using PT = typename std::conditional<P16, uint16_t, uint32_t>::type;
+  if (P16) qs_build_profile_paired<R>(smem_prof, p, qp.m);
+  else qs_build_profile<R, uint32_t>(smem_prof, p, qp.m);
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int L = p.L;
@@ -150,7 +195,7 @@ __global__ void __launch_bounds__(128) qs_score_kernel(const QsParams qp) {
   const bool live = pair < p.npairs;
   if (!live) pair = p.npairs - 1;        // keep the lane in the shuffles; it stores nothing
   const PairDesc pd = p.pairs[pair];
-  QsWavefront<R, SAT, uint32_t> wf(p);
+  QsWavefront<R, SAT, PT> wf(p);
   wf.L = L; wf.g = g; wf.lane = lane;
   wf.prepare(pd, 0, smem_prof);
   const int steps = warp_max_i32((int)pd.nblk << p.logB);
@@ -180,7 +225,7 @@ __global__ void __launch_bounds__(128) qs_score_kernel(const QsParams qp) {
 template <int R, bool SAT>
 __global__ void __launch_bounds__(128, SWB_TRACE_MINBLOCKS) qs_trace_kernel(const QsTraceParams qp) {
   extern __shared__ uint32_t smem_prof[];
-  qs_build_profile<R, uint16_t>(smem_prof, qp.tp.pp, qp.m);
+  qs_build_profile_paired<R>(smem_prof, qp.tp.pp, qp.m);
   trace_body<R, 1, SAT, true, true, QsWavefront<R, SAT, uint16_t>>(qp.tp, smem_prof, qp.m);
 }
 

@@ -34,7 +34,7 @@ KERNELS = {
     "c1x64/c2x64  score_kernel<R=16,C=1,SAT,profile>  (8 lanes x 16 rows)": ("sw_inst_r16.o", "_ZN3swb12score_kernelILi16ELi1ELi1ELb1EEEvNS_10PassParamsE", 2 * 16 * 1),
     "c1/c2 x1  score_kernel<R=4,C=2,SAT,profile>  (32 lanes x 4 rows, 2 columns)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi2ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 2),
     "c2 x1  score_kernel<R=4,C=1,SAT,profile>  (32 lanes x 4 rows)": ("sw_inst_r4.o", "_ZN3swb12score_kernelILi4ELi1ELi1ELb1EEEvNS_10PassParamsE", 2 * 4 * 1),
-    "c4  qs_score_kernel<R=19,EXACT>  (16 lanes x 19 rows, query-stationary)": ("sw_inst_r19.o", "_ZN3swb15qs_score_kernelILi19ELb0EEEvNS_8QsParamsE", 2 * 19 * 1),
+    "c4  qs_score_kernel<R=19,EXACT,paired 16-bit profile>  (16 lanes x 19 rows, query-stationary)": ("sw_inst_r19.o", "_ZN3swb15qs_score_kernelILi19ELb0ELb1EEEvNS_8QsParamsE", 2 * 19 * 1),
     "c5  score_units_kernel<R=5,C=8,EXACT,profile>  (pipelined strips, SWB_STRIP_R=5)": ("sw_inst_r5.o", "_ZN3swb18score_units_kernelILi5ELi8ELi0ELb1EEEvNS_10PassParamsE", 2 * 5 * 8),
     "c5  score_units_kernel<R=5,C=8,SAT,profile>  (pipelined strips, SWB_STRIP_R=5)": ("sw_inst_r5.o", "_ZN3swb18score_units_kernelILi5ELi8ELi1ELb1EEEvNS_10PassParamsE", 2 * 5 * 8),
     "c5  score_units_kernel<R=4,C=8,EXACT,profile>  (pipelined strips, 32 lanes x 4 rows, 8 columns)": ("sw_inst_r4.o", "_ZN3swb18score_units_kernelILi4ELi8ELi0ELb1EEEvNS_10PassParamsE", 2 * 4 * 8),
