@@ -205,6 +205,28 @@ def test_bench_peaks_and_metric_contract():
     assert b.OPS_PER_CELL["SAT_U8"] == 9 and b.OPS_PER_CELL["EXACT"] == 8
 
 
+def test_issue_fraction_uses_executed_counts_for_the_pipelined_strip_kernel():
+    """The SASS loop of score_units_kernel holds polling and slow paths that are not taken in the steady state, so its
+    roofline fraction must come from the EXECUTED instruction counts (ncu capture, tagged from_profile) — and equal the
+    ALU-pipe utilisation that capture measured; every other kernel is counted from the SASS of the build."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    counts, src = b.load_sass_counts()
+    assert src and counts
+    p_int = 18.5238
+    # the geometry and timing of the ncu capture at 10 kbp x 51 Mbp (profiles/score_units_kernel_r02_c5_ncu.txt (2))
+    cells = 79 * 128 * 51_003_392 * 2 * 8
+    st = {"kernel_kind": 1, "rows_per_lane": 4, "cols_per_step": 8, "cells_executed": cells, "pass1_us": 2.019096e6}
+    fr = b.issue_fraction(counts, st, False, p_int)
+    assert fr["counts_from"].startswith("from_profile") and fr["alu_inst_per_cell_pair"] < fr["alu_inst_per_cell_pair_static_sass"]
+    assert abs(fr["frac"] - 0.364) < 0.01, fr            # ncu: ALU pipe 36.4 % busy
+    st3 = {"kernel_kind": 0, "rows_per_lane": 19, "cols_per_step": 1, "cells_executed": 10 ** 13, "pass1_us": 1.0e6}
+    fr3 = b.issue_fraction(counts, st3, True, p_int)
+    assert fr3["counts_from"].startswith("SASS") and 3.5 < fr3["alu_inst_per_cell_pair"] < 4.0
+
+
 def test_sass_counts_match_the_build():
     """profiles/sass_counts_r02.json (the instruction counts bench.py's issue-based roofline fraction uses) is what
     tools/sass_counts.py computes from the objects of the current build."""
